@@ -1,0 +1,255 @@
+// Decode-side kernels: greedy argmax + next-token embedding, row log-sum-exp, beam top-k with
+// backpointers, beam state reorder and final backtrack.  No host synchronisation anywhere
+// (the reference copies the argmax to the host every step, depth_models.py:298-299).
+#pragma once
+#include "common.cuh"
+
+namespace dic {
+
+// ---- initial state: replicate (h0,c0) over the rows of each image, embed <start> ---------------
+template <typename ST>
+__global__ void __launch_bounds__(256) decode_init_kernel(const float* __restrict__ h0,
+                                                          const float* __restrict__ c0,
+                                                          const ST* __restrict__ emb, int start_id,
+                                                          ST* __restrict__ X, long long x_row, int col_h,
+                                                          float* __restrict__ c, int rows, int KB, int E,
+                                                          int H) {
+  const int W = E + H;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < rows * W; i += gridDim.x * 256) {
+    const int r = i / W, q = i - r * W;
+    const int b = r / KB;
+    if (q < E) {
+      X[(size_t)r * x_row + q] = emb[(size_t)start_id * E + q];
+    } else {
+      const int j = q - E;
+      X[(size_t)r * x_row + col_h + j] = from_f<ST>(h0[(size_t)b * H + j]);
+      c[(size_t)r * H + j] = c0[(size_t)b * H + j];
+    }
+  }
+}
+
+// ---- greedy: token = argmax_v logits[r,v] (ties -> lowest id), then embed it ---------------------
+// The reference takes argmax(softmax(logits)) (depth_models.py:296-297); softmax is monotone,
+// so the argmax of the logits is the same token except on fp32 rounding ties.
+template <typename ST>
+__global__ void __launch_bounds__(256) argmax_embed_kernel(const float* __restrict__ logits, int V,
+                                                           int64_t* __restrict__ tokens,
+                                                           long long tok_stride, const ST* __restrict__ emb,
+                                                           int E, ST* __restrict__ Xnext, long long x_row) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ int s_tok;
+  const int r = blockIdx.x;
+  const float* lg = logits + (size_t)r * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float x = lg[v];
+    if (x > best) { best = x; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    if (bi == 0x7fffffff) bi = 0;
+    s_tok = bi;
+    tokens[(size_t)r * tok_stride] = bi;
+  }
+  __syncthreads();
+  const int tok = s_tok;
+  for (int e = threadIdx.x; e < E; e += 256) Xnext[(size_t)r * x_row + e] = emb[(size_t)tok * E + e];
+}
+
+// ---- lse[r] = log sum_v exp(logits[r,v]) -------------------------------------------------------
+__global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ logits, int V,
+                                                      float* __restrict__ lse) {
+  __shared__ float scratch[64];
+  const int r = blockIdx.x;
+  const float* lg = logits + (size_t)r * V;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += 256) m = fmaxf(m, lg[v]);
+  m = block_max(m, scratch);
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) s += expf(lg[v] - m);
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) lse[r] = m + logf(s);
+}
+
+// ---- beam selection ----------------------------------------------------------------------------
+// cand[j*V+v] = scores[j] + (logits[j,v] - lse[j]); finished rows keep only <end> at cost 0.
+// Stable top-K: order by (value desc, flat index asc) -- bit-exact w.r.t. the oracle's
+// beam_select given identical inputs (plain fp32 add/sub, round-to-nearest, no contraction).
+struct Cand {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) {
+  return v > bv || (v == bv && i < bi);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict__ scores,
+                                                        const uint8_t* __restrict__ finished,
+                                                        const float* __restrict__ logits,
+                                                        const float* __restrict__ lse, int V, int end_id,
+                                                        float* __restrict__ new_scores,
+                                                        int32_t* __restrict__ back, int32_t* __restrict__ tok,
+                                                        uint8_t* __restrict__ new_finished) {
+  __shared__ float s_sc[K], s_lse[K];
+  __shared__ uint8_t s_fin[K];
+  __shared__ float wv[8];
+  __shared__ int wi[8];
+  __shared__ int s_win;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < K) {
+    s_sc[tid] = scores[b * K + tid];
+    s_lse[tid] = lse[b * K + tid];
+    s_fin[tid] = finished[b * K + tid];
+  }
+  __syncthreads();
+
+  float lv[K];
+  int li[K];
+#pragma unroll
+  for (int q = 0; q < K; ++q) { lv[q] = -INFINITY; li[q] = 0x7fffffff; }
+
+  for (int j = 0; j < K; ++j) {
+    const float sc = s_sc[j], ls = s_lse[j];
+    const bool fin = s_fin[j] != 0;
+    const float* lg = logits + ((size_t)b * K + j) * V;
+    for (int v = tid; v < V; v += 256) {
+      float c;
+      if (fin) c = (v == end_id) ? sc : -INFINITY;
+      else c = __fadd_rn(sc, __fsub_rn(lg[v], ls));
+      const int fi = j * V + v;
+      if (cand_better(c, fi, lv[K - 1], li[K - 1])) {
+        lv[K - 1] = c; li[K - 1] = fi;
+#pragma unroll
+        for (int q = K - 1; q > 0; --q) {
+          if (cand_better(lv[q], li[q], lv[q - 1], li[q - 1])) {
+            const float tv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = tv;
+            const int ti = li[q]; li[q] = li[q - 1]; li[q - 1] = ti;
+          }
+        }
+      }
+    }
+  }
+
+  // K rounds of block-wide arg-best over the heads of the per-thread sorted lists
+  for (int r = 0; r < K; ++r) {
+    float hv = lv[0];
+    int hi = li[0];
+    float bv = hv;
+    int bi = hi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (cand_better(wv[w], wi[w], bv, bi)) { bv = wv[w]; bi = wi[w]; }
+      s_win = bi;
+      const int jb = bi / V, tk = bi - jb * V;
+      new_scores[b * K + r] = bv;
+      back[b * K + r] = jb;
+      tok[b * K + r] = tk;
+      new_finished[b * K + r] = (uint8_t)((s_fin[jb] != 0) || (tk == end_id));
+    }
+    __syncthreads();
+    if (hi == s_win) {  // pop the winner's head (flat indices are unique)
+#pragma unroll
+      for (int q = 0; q < K - 1; ++q) { lv[q] = lv[q + 1]; li[q] = li[q + 1]; }
+      lv[K - 1] = -INFINITY; li[K - 1] = 0x7fffffff;
+    }
+    __syncthreads();
+  }
+}
+
+inline int launch_beam_topk(const float* scores, const uint8_t* finished, const float* logits,
+                            const float* lse, int B, int K, int V, int end_id, float* new_scores,
+                            int32_t* back, int32_t* tok, uint8_t* new_finished, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (K > V) DIC_FAIL(-4, "beam %d larger than vocabulary %d", K, V);
+#define DIC_TOPK_CASE(KK)                                                                       \
+  case KK:                                                                                      \
+    beam_topk_kernel<KK><<<B, 256, 0, st>>>(scores, finished, logits, lse, V, end_id, new_scores, \
+                                            back, tok, new_finished);                           \
+    break;
+  switch (K) {
+    DIC_TOPK_CASE(1) DIC_TOPK_CASE(2) DIC_TOPK_CASE(3) DIC_TOPK_CASE(4)
+    DIC_TOPK_CASE(5) DIC_TOPK_CASE(6) DIC_TOPK_CASE(7) DIC_TOPK_CASE(8)
+    default: DIC_FAIL(-4, "beam size %d not in 1..%d", K, DIC_MAX_BEAM);
+  }
+#undef DIC_TOPK_CASE
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- beam reorder: gather (h,c) by backpointer, embed the chosen tokens ------------------------------
+template <typename ST>
+__global__ void __launch_bounds__(256) beam_reorder_kernel(const ST* __restrict__ h_tmp,
+                                                           const float* __restrict__ c_tmp,
+                                                           const int32_t* __restrict__ back,
+                                                           const int32_t* __restrict__ tok,
+                                                           const ST* __restrict__ emb,
+                                                           ST* __restrict__ Xnext, long long x_row, int col_h,
+                                                           float* __restrict__ c, int rows, int K, int E,
+                                                           int H) {
+  const int W = E + H;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < rows * W; i += gridDim.x * 256) {
+    const int r = i / W, q = i - r * W;
+    if (q < E) {
+      Xnext[(size_t)r * x_row + q] = emb[(size_t)tok[r] * E + q];
+    } else {
+      const int j = q - E;
+      const int src = (r / K) * K + back[r];
+      Xnext[(size_t)r * x_row + col_h + j] = h_tmp[(size_t)src * H + j];
+      c[(size_t)r * H + j] = c_tmp[(size_t)src * H + j];
+    }
+  }
+}
+
+// ---- final backtrack from row 0 (top-k output is sorted, so row 0 is the best hypothesis) --------
+__global__ void __launch_bounds__(128) beam_backtrack_kernel(const int32_t* __restrict__ back,
+                                                             const int32_t* __restrict__ tok,
+                                                             const float* __restrict__ final_scores, int B,
+                                                             int K, int T, int end_id,
+                                                             int64_t* __restrict__ tokens,
+                                                             int32_t* __restrict__ lengths,
+                                                             float* __restrict__ scores) {
+  const int b = blockIdx.x * 128 + threadIdx.x;
+  if (b >= B) return;
+  int row = 0;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t o = ((size_t)t * B + b) * K + row;
+    tokens[(size_t)b * T + t] = tok[o];
+    row = back[o];
+  }
+  int len = T;
+  for (int t = 0; t < T; ++t)
+    if (tokens[(size_t)b * T + t] == end_id) { len = t + 1; break; }
+  lengths[b] = len;
+  scores[b] = final_scores[b * K];
+}
+
+__global__ void __launch_bounds__(256) beam_state_init_kernel(float* scores, uint8_t* finished, int B, int K) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= B * K) return;
+  scores[i] = (i % K == 0) ? 0.f : -INFINITY;
+  finished[i] = 0;
+}
+
+}  // namespace dic

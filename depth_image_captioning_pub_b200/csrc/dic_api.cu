@@ -1,0 +1,807 @@
+// C-ABI entry points (include/dic.h) and the host-side orchestration of the decoder path.
+// One translation unit: kernels are header templates, this file instantiates and sequences them.
+#include "attention.cuh"
+#include "common.cuh"
+#include "decode.cuh"
+#include "gemm_generic.cuh"
+#include "gemm_tc.cuh"
+#include "layout.cuh"
+#include "lstm.cuh"
+#include "misc.cuh"
+
+namespace dic {
+thread_local char g_err[512] = {0};
+
+static int check_dims(const dic_dims* d, int dtype) {
+  if (!d) DIC_FAIL(-1, "dims is null");
+  if (dtype != DIC_F32 && dtype != DIC_BF16) DIC_FAIL(-1, "bad dtype %d", dtype);
+  if (d->L <= 0 || d->D <= 0 || d->A <= 0 || d->E <= 0 || d->H <= 0 || d->V <= 0)
+    DIC_FAIL(-1, "non-positive dimension");
+  if (d->D % 8 || d->A % 4 || d->E % 4 || d->H % 4) DIC_FAIL(-1, "need D%%8==0, A,E,H%%4==0");
+  if (dtype == DIC_BF16 && (d->E % 8 || d->H % 8 || d->A % 8))
+    DIC_FAIL(-1, "bf16 mode needs A,E,H %% 8 == 0");
+  if (d->A > 1024 || d->L > 1024) DIC_FAIL(-1, "A and L must be <= 1024");
+  return 0;
+}
+
+static int make_sizes(const int32_t* host_bs, int T, int B, StepSizes* s, int* total) {
+  if (T <= 0 || T > DIC_MAX_STEPS) DIC_FAIL(-1, "T=%d out of range 1..%d", T, DIC_MAX_STEPS);
+  int tot = 0, prev = B;
+  for (int t = 0; t < DIC_MAX_STEPS; ++t) s->n[t] = 0;
+  for (int t = 0; t < T; ++t) {
+    const int n = host_bs[t];
+    if (n <= 0 || n > prev) DIC_FAIL(-1, "batch_sizes must be positive and non-increasing (t=%d n=%d)", t, n);
+    s->n[t] = n;
+    prev = n;
+    tot += n;
+  }
+  *total = tot;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM dispatch: tcgen05 engine for bf16 K-major operands of suitable shape, FMA engine otherwise.
+// ---------------------------------------------------------------------------------------------
+static int gemm(const GemmArgs& g, cudaStream_t st) {
+  if (tc_gemm_eligible(g)) return tc_gemm(g, st);
+  return gemm_generic(g, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared prologue: Fsum, meanF, att1 (K0)
+// ---------------------------------------------------------------------------------------------
+template <typename ST>
+static int prologue(const dic_dims& d, const Pack& pk, const void* f_rgb, const void* f_depth,
+                    int feat_dtype, int B, ST* Fsum, float* meanF, ST* att1, const ST** Fuse,
+                    cudaStream_t st) {
+  const int is_bf16 = sizeof(ST) == 2;
+  const bool alias = (f_depth == nullptr) && ((feat_dtype == DIC_BF16) == (is_bf16 != 0));
+  // base decoders with matching storage: no copy, only the mean (base_caption_models.py:118)
+  DIC_TRY(launch_fuse_feats<ST>(f_rgb, f_depth, feat_dtype == DIC_BF16, alias ? nullptr : Fsum, meanF, B,
+                                d.L, d.D, st));
+  const ST* F = alias ? reinterpret_cast<const ST*>(f_rgb) : Fsum;
+  *Fuse = F;
+  // att1 = F . W_enc^T + b_enc   (attention.py:84, hoisted out of the time loop)
+  GemmArgs g = gemm_args_nt(F, is_bf16, d.D, pk.Wenc(), is_bf16, d.D, att1, is_bf16, d.A, B * d.L, d.A,
+                            d.D, pk.b_enc());
+  DIC_TRY(gemm(g, st));
+  return 0;
+}
+
+template <typename ST>
+static int init_state_gemm(const dic_dims& d, const Pack& pk, const float* meanF, int B, void* h_out,
+                           int h_bf16, long long h_ld, float* c_out, cudaStream_t st) {
+  const int is_bf16 = sizeof(ST) == 2;
+  // h0, c0 = chunk(init_linear(mean_l F), 2)   (depth_models.py:166-168)
+  GemmArgs g = gemm_args_nt(meanF, 0, d.D, pk.Winit(), is_bf16, d.D, h_out, h_bf16, h_ld, B, d.H, d.D,
+                            pk.b_init());
+  DIC_TRY(gemm_generic(g, st));
+  const char* w2 = reinterpret_cast<const char*>(pk.Winit()) + (size_t)d.H * d.D * sizeof(ST);
+  g = gemm_args_nt(meanF, 0, d.D, w2, is_bf16, d.D, c_out, 0, d.H, B, d.H, d.D, pk.b_init() + d.H);
+  DIC_TRY(gemm_generic(g, st));
+  return 0;
+}
+
+// h-projection of a step: [att2 | beta] = [h W_dec^T + b_dec | sigmoid(h W_beta^T + b_beta)]
+// (attention.py:85, depth_models.py:189)
+template <typename ST>
+static int hproj(const dic_dims& d, const Pack& pk, const ST* h, long long h_ld, int rows, float* HP,
+                 cudaStream_t st) {
+  const int is_bf16 = sizeof(ST) == 2;
+  GemmArgs g = gemm_args_nt(h, is_bf16, h_ld, pk.Wdb(d), is_bf16, d.H, HP, 0, d.A + d.D, rows,
+                            d.A + d.D, d.H, pk.bias_db());
+  g.sig_lo = d.A;
+  g.sig_hi = d.A + d.D;
+  return gemm(g, st);
+}
+
+// gate pre-activations as split-K partials: [emb|zg|h] . [W_ih|W_hh]^T  (nn.LSTMCell)
+template <typename ST>
+static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long XW, int rows,
+                      int rows_alloc, float* gate_part, int* splits_out, cudaStream_t st) {
+  const int is_bf16 = sizeof(ST) == 2;
+  GemmArgs g = gemm_args_nt(X, is_bf16, XW, pk.Wg(), is_bf16, XW, gate_part, 0, 4 * d.H, rows, 4 * d.H,
+                            (int)XW, nullptr);
+  int s = pick_splits(rows, 4 * d.H, (int)XW);
+  if (s > kGateSplitsMax) s = kGateSplitsMax;
+  g.splits = s;
+  g.split_mode = 1;
+  g.split_stride = (long long)rows_alloc * 4 * d.H;
+  *splits_out = s;
+  return gemm_generic(g, st);
+}
+
+// =============================================================================================
+// training forward
+// =============================================================================================
+template <typename ST>
+static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pack, const void* f_rgb,
+                                const void* f_depth, int feat_dtype, const int64_t* captions,
+                                int cap_stride, const StepSizes& sizes, int total, int T, int B,
+                                const float* u, float temp, const float* dropout_mask, float* logits,
+                                float* alphas, char* ws, cudaStream_t st) {
+  const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
+  const int is_bf16 = sizeof(ST) == 2;
+  const Pack pk(pack, d, dtype);
+  const TrainLayout lay(d, dtype, B, T);
+  const size_t XW = lay.XW;
+  ST* Fsum = reinterpret_cast<ST*>(ws + lay.Fsum);
+  float* meanF = reinterpret_cast<float*>(ws + lay.meanF);
+  ST* att1 = reinterpret_cast<ST*>(ws + lay.att1);
+  ST* XH = reinterpret_cast<ST*>(ws + lay.XH);
+  float* HP = reinterpret_cast<float*>(ws + lay.HP);
+  float* Z = reinterpret_cast<float*>(ws + lay.Z);
+  float* acts = reinterpret_cast<float*>(ws + lay.acts);
+  float* c_all = reinterpret_cast<float*>(ws + lay.c_all);
+  float* gate_part = reinterpret_cast<float*>(ws + lay.gate_part);
+  ST* Hdrop = reinterpret_cast<ST*>(ws + lay.Hdrop);
+
+  // invalid (b >= bs_valid) rows of the step buffers must stay finite zeros: the post-loop
+  // weight-gradient GEMMs run over all T*B rows.
+  DIC_CUDA(cudaMemsetAsync(XH, 0, ((size_t)T * B + B) * XW * sizeof(ST), st));
+
+  const ST* F = nullptr;
+  DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, att1, &F, st));
+  DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, XH + d.E + d.D, is_bf16, (long long)XW, c_all, st));
+
+  // all-step embedding gather (depth_models.py:160)
+  {
+    dim3 grid(cdiv(B * d.E, 256), T);
+    embed_gather_tf_kernel<ST><<<grid, 256, 0, st>>>(reinterpret_cast<const ST*>(pk.Emb()), captions,
+                                                     cap_stride, XH, (long long)XW, (long long)B * XW, B,
+                                                     d.E, d.V, sizes, T);
+    DIC_LAUNCH_CHECK();
+  }
+
+  int off = 0;
+  for (int t = 0; t < T; ++t) {
+    const int n = sizes.n[t];
+    ST* X = XH + (size_t)t * B * XW;
+    ST* Xn = XH + (size_t)(t + 1) * B * XW;
+    float* HPt = HP + (size_t)t * B * (d.A + d.D);
+    DIC_TRY(hproj<ST>(d, pk, X + d.E + d.D, (long long)XW, n, HPt, st));
+
+    AttnFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.F = F; a.att1 = att1; a.hp = HPt; a.w_full = pk.w_full(); a.b_full = pk.b_full();
+    a.u = u ? u + (size_t)off * d.L : nullptr;
+    a.alpha_out = alphas + (size_t)t * d.L;
+    a.alpha_stride = (long long)T * d.L;
+    a.z_out = Z + (size_t)t * B * d.D;
+    a.zg_out = X + d.E;
+    a.zg_stride = (long long)XW;
+    a.L = d.L; a.D = d.D; a.A = d.A;
+    a.mode = attn_mode;
+    a.inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
+    DIC_TRY(launch_attn_step<ST>(a, n, 1, st));
+
+    int splits = 1;
+    DIC_TRY(gates_gemm<ST>(d, pk, X, (long long)XW, n, B, gate_part, &splits, st));
+
+    LstmFwdArgs l;
+    memset(&l, 0, sizeof(l));
+    l.gate_part = gate_part; l.part_stride = (long long)B * 4 * d.H; l.splits = splits;
+    l.bias_g = pk.bias_g();
+    l.c_in = c_all + (size_t)t * B * d.H;
+    l.c_out = c_all + (size_t)(t + 1) * B * d.H;
+    l.acts = acts + (size_t)t * B * 4 * d.H;
+    l.h_out = Xn + d.E + d.D; l.h_stride = (long long)XW;
+    l.hdrop_out = Hdrop + (size_t)off * d.H;
+    l.mask = dropout_mask ? dropout_mask + (size_t)off * d.H : nullptr;
+    l.rows = n; l.H = d.H;
+    DIC_TRY(launch_lstm_fwd<ST>(l, st));
+    off += n;
+  }
+
+  // logits for every packed row at once: linear(dropout(h)) (depth_models.py:197), written in
+  // PackedSequence (time-major) order
+  GemmArgs g = gemm_args_nt(Hdrop, is_bf16, d.H, pk.Wout(), is_bf16, d.H, logits, 0, d.V, total, d.V, d.H,
+                            pk.b_out());
+  DIC_TRY(gemm(g, st));
+  return 0;
+}
+
+// =============================================================================================
+// training backward
+// =============================================================================================
+template <typename ST>
+static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* pack,
+                                 const int64_t* captions, int cap_stride, const StepSizes& sizes,
+                                 int total, int T, int B, const float* d_logits, const float* d_alphas,
+                                 const float* alphas, float temp, const float* dropout_mask,
+                                 const dic_params& gr, float* d_feats, const void* f_rgb_alias, char* ws,
+                                 cudaStream_t st) {
+  const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
+  const int is_bf16 = sizeof(ST) == 2;
+  const Pack pk(pack, d, dtype);
+  const TrainLayout lay(d, dtype, B, T);
+  const long long XW = (long long)lay.XW, GW = (long long)lay.GW;
+  const int H = d.H, A = d.A, D = d.D, E = d.E, L = d.L, V = d.V;
+  const size_t TB = (size_t)T * B;
+  const ST* F = f_rgb_alias ? reinterpret_cast<const ST*>(f_rgb_alias) : reinterpret_cast<ST*>(ws + lay.Fsum);
+  float* meanF = reinterpret_cast<float*>(ws + lay.meanF);
+  ST* att1 = reinterpret_cast<ST*>(ws + lay.att1);
+  ST* XH = reinterpret_cast<ST*>(ws + lay.XH);
+  float* HP = reinterpret_cast<float*>(ws + lay.HP);
+  float* Z = reinterpret_cast<float*>(ws + lay.Z);
+  float* acts = reinterpret_cast<float*>(ws + lay.acts);
+  float* c_all = reinterpret_cast<float*>(ws + lay.c_all);
+  ST* Hdrop = reinterpret_cast<ST*>(ws + lay.Hdrop);
+  ST* G = reinterpret_cast<ST*>(ws + lay.G);
+  ST* DZ = reinterpret_cast<ST*>(ws + lay.DZ);
+  float* de = reinterpret_cast<float*>(ws + lay.de);
+  float* dzg = reinterpret_cast<float*>(ws + lay.dzg);
+  float* dh = reinterpret_cast<float*>(ws + lay.dh);
+  float* dc = reinterpret_cast<float*>(ws + lay.dc);
+  float* dHout = reinterpret_cast<float*>(ws + lay.dHout);
+  float* dwfull_part = reinterpret_cast<float*>(ws + lay.dwfull_part);
+  float* dbfull_part = reinterpret_cast<float*>(ws + lay.dbfull_part);
+  ST* datt1 = reinterpret_cast<ST*>(ws + lay.datt1);
+  float* dXemb = reinterpret_cast<float*>(ws + lay.dXemb);
+  float* dmeanF = reinterpret_cast<float*>(ws + lay.dmeanF);
+
+  if (attn_mode == DIC_ATTN_GUMBEL_MAX) DIC_FAIL(-1, "gumbel-max (Hard_sample) is a no_grad path");
+
+  DIC_CUDA(cudaMemsetAsync(G, 0, TB * GW * sizeof(ST), st));
+  DIC_CUDA(cudaMemsetAsync(DZ, 0, TB * D * sizeof(ST), st));
+  DIC_CUDA(cudaMemsetAsync(de, 0, TB * L * sizeof(float), st));
+  DIC_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * B * H, st));
+  DIC_CUDA(cudaMemsetAsync(dc, 0, sizeof(float) * B * H, st));
+  DIC_CUDA(cudaMemsetAsync(dwfull_part, 0, sizeof(float) * TB * A, st));
+  DIC_CUDA(cudaMemsetAsync(dbfull_part, 0, sizeof(float) * TB, st));
+
+  // dHout = d_logits . W_out   (all packed rows)
+  {
+    GemmArgs g = gemm_args_nt(d_logits, 0, V, pk.Wout(), is_bf16, 0, dHout, 0, H, total, H, V, nullptr);
+    g.b_n = 1; g.b_k = H;
+    DIC_TRY(gemm(g, st));
+  }
+
+  const float inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
+  int off = total;
+  for (int t = T - 1; t >= 0; --t) {
+    const int n = sizes.n[t];
+    off -= n;
+    ST* Gt = G + (size_t)t * B * GW;
+    float* HPt = HP + (size_t)t * B * (A + D);
+
+    LstmBwdArgs lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.dh_carry = dh; lb.dh_out = dHout + (size_t)off * H;
+    lb.mask = dropout_mask ? dropout_mask + (size_t)off * H : nullptr;
+    lb.dc_carry = dc;
+    lb.acts = acts + (size_t)t * B * 4 * H;
+    lb.c_new = c_all + (size_t)(t + 1) * B * H;
+    lb.c_prev = c_all + (size_t)t * B * H;
+    lb.G = Gt; lb.g_stride = GW; lb.rows = n; lb.H = H;
+    DIC_TRY(launch_lstm_bwd<ST>(lb, st));
+
+    // dzg = dgates . W_ih[:, E:E+D]
+    {
+      GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, reinterpret_cast<const ST*>(pk.Wg()) + E, is_bf16, 0, dzg,
+                                0, D, n, D, 4 * H, nullptr);
+      g.b_n = 1; g.b_k = XW;
+      DIC_TRY(gemm(g, st));
+    }
+
+    AttnBwdArgs ab;
+    memset(&ab, 0, sizeof(ab));
+    ab.F = F; ab.att1 = att1; ab.hp = HPt;
+    ab.z = Z + (size_t)t * B * D; ab.dzg = dzg;
+    ab.alpha = alphas + (size_t)t * L; ab.alpha_stride = (long long)T * L;
+    ab.dalpha = d_alphas ? d_alphas + (size_t)t * L : nullptr;
+    ab.w_full = pk.w_full();
+    ab.G = Gt; ab.g_stride = GW; ab.gcol_att2 = 4 * H; ab.gcol_beta = 4 * H + A;
+    ab.DZ = DZ + (size_t)t * B * D;
+    ab.de_out = de + (size_t)t * B * L;
+    ab.dwfull_part = dwfull_part + (size_t)t * B * A;
+    ab.dbfull_part = dbfull_part + (size_t)t * B;
+    ab.L = L; ab.D = D; ab.A = A; ab.inv_temp = inv_temp;
+    DIC_TRY(launch_attn_bwd<ST>(ab, n, st));
+
+    // dh_{t-1} = [dgates | datt2 | dbeta'] . [W_hh ; W_dec ; W_beta]
+    {
+      GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, pk.Whdb(), is_bf16, 0, dh, 0, H, n, H, (int)GW, nullptr);
+      g.b_n = 1; g.b_k = H;
+      DIC_TRY(gemm(g, st));
+    }
+  }
+
+  // ---- post-loop: everything that is a sum over (t, b) is one contraction over T*B rows ----
+  // init_linear: rows [0,H) from dh0, rows [H,2H) from dc0
+  for (int half = 0; half < 2; ++half) {
+    const float* dsrc = half == 0 ? dh : dc;
+    GemmArgs g = gemm_args_nt(dsrc, 0, 0, meanF, 0, 0, gr.init_w + (size_t)half * H * D, 0, D, H, D, B, nullptr);
+    g.a_m = 1; g.a_k = H; g.b_n = 1; g.b_k = D;
+    DIC_TRY(gemm_generic(g, st));
+    DIC_TRY(launch_colsum(dsrc, 0, B, H, H, gr.init_b + half * H, st));
+    if (d_feats) {
+      GemmArgs m = gemm_args_nt(dsrc, 0, H, reinterpret_cast<const ST*>(pk.Winit()) + (size_t)half * H * D,
+                                is_bf16, 0, dmeanF, 0, D, B, D, H, nullptr);
+      m.b_n = 1; m.b_k = D; m.accumulate = half;
+      DIC_TRY(gemm_generic(m, st));
+    }
+  }
+
+  // biases of the LSTM / decoder_att / f_beta: column sums of G
+  DIC_TRY(launch_colsum(G, is_bf16, (int)TB, 4 * H, GW, gr.b_ih, st));
+  DIC_CUDA(cudaMemcpyAsync(gr.b_hh, gr.b_ih, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+  DIC_TRY(launch_colsum(G + 4 * H, is_bf16, (int)TB, A, GW, gr.dec_att_b, st));
+  DIC_TRY(launch_colsum(G + 4 * H + A, is_bf16, (int)TB, D, GW, gr.fbeta_b, st));
+
+  auto wgrad = [&](const ST* Aop, long long a_ld, int M, const ST* Bop, long long b_ld, int N, int K,
+                   float* C, long long ldc) -> int {
+    DIC_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
+    GemmArgs g = gemm_args_nt(Aop, is_bf16, 0, Bop, is_bf16, 0, C, 0, ldc, M, N, K, nullptr);
+    g.a_m = 1; g.a_k = a_ld; g.b_n = 1; g.b_k = b_ld;
+    g.splits = pick_splits(M, N, K);
+    g.split_mode = 0;
+    return gemm(g, st);
+  };
+  // [dW_ih | dW_hh] = dgates^T . [emb|zg|h]
+  DIC_TRY(wgrad(G, GW, 4 * H, XH, XW, E + D, (int)TB, gr.w_ih, E + D));
+  DIC_TRY(wgrad(G, GW, 4 * H, XH + E + D, XW, H, (int)TB, gr.w_hh, H));
+  // dW_dec = datt2^T . h_prev ; dW_beta = dbeta'^T . h_prev
+  DIC_TRY(wgrad(G + 4 * H, GW, A, XH + E + D, XW, H, (int)TB, gr.dec_att_w, H));
+  DIC_TRY(wgrad(G + 4 * H + A, GW, D, XH + E + D, XW, H, (int)TB, gr.fbeta_w, H));
+
+  // embedding: dX_emb = dgates . W_ih[:, :E], scattered by token id
+  {
+    GemmArgs g = gemm_args_nt(G, is_bf16, GW, pk.Wg(), is_bf16, 0, dXemb, 0, E, (int)TB, E, 4 * H, nullptr);
+    g.b_n = 1; g.b_k = XW;
+    DIC_TRY(gemm(g, st));
+    DIC_CUDA(cudaMemsetAsync(gr.embed_w, 0, sizeof(float) * (size_t)V * E, st));
+    dim3 grid(cdiv(B * E, 256), T);
+    embed_scatter_add_kernel<<<grid, 256, 0, st>>>(dXemb, captions, cap_stride, gr.embed_w, B, E, V, sizes, T);
+    DIC_LAUNCH_CHECK();
+  }
+
+  // full_att
+  DIC_TRY(launch_colsum(dwfull_part, 0, (int)TB, A, A, gr.full_att_w, st));
+  DIC_TRY(launch_colsum(dbfull_part, 0, (int)TB, 1, 1, gr.full_att_b, st));
+
+  // encoder_att: datt1 summed over steps, then two contractions over B*L rows
+  {
+    Datt1Args da;
+    da.att1 = att1; da.hp_all = HP; da.de_all = de; da.w_full = pk.w_full(); da.datt1 = datt1;
+    da.B = B; da.L = L; da.D = D; da.A = A; da.T = T; da.sizes = sizes;
+    DIC_TRY(launch_datt1<ST>(da, st));
+    DIC_TRY(launch_colsum(datt1, is_bf16, B * L, A, A, gr.enc_att_b, st));
+    DIC_TRY(wgrad(datt1, A, A, F, D, D, B * L, gr.enc_att_w, D));
+  }
+
+  // linear (vocabulary projection)
+  {
+    DIC_CUDA(cudaMemsetAsync(gr.lin_w, 0, sizeof(float) * (size_t)V * H, st));
+    GemmArgs g = gemm_args_nt(d_logits, 0, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
+    g.a_m = 1; g.a_k = V; g.b_n = 1; g.b_k = H;
+    g.splits = pick_splits(V, H, total);
+    DIC_TRY(gemm(g, st));
+    DIC_TRY(launch_colsum(d_logits, 0, total, V, V, gr.lin_b, st));
+  }
+
+  // dL/dF = datt1 . W_enc + sum_t alpha_t (x) dz_t + dmeanF / L
+  if (d_feats) {
+    GemmArgs g = gemm_args_nt(datt1, is_bf16, A, pk.Wenc(), is_bf16, 0, d_feats, 0, D, B * L, D, A, nullptr);
+    g.b_n = 1; g.b_k = D;
+    DIC_TRY(gemm(g, st));
+    GemmArgs g2 = gemm_args_nt(alphas, 0, 0, DZ, is_bf16, 0, d_feats, 0, D, L, D, T, dmeanF);
+    g2.a_m = 1; g2.a_k = L; g2.a_batch = (long long)T * L;
+    g2.b_n = 1; g2.b_k = (long long)B * D; g2.b_batch = D;
+    g2.c_batch = (long long)L * D;
+    g2.bias_batch = D; g2.bias_scale = 1.f / (float)L;
+    g2.batch = B;
+    g2.accumulate = 1;
+    DIC_TRY(gemm_generic(g2, st));
+  }
+  return 0;
+}
+
+// =============================================================================================
+// decoding (greedy and beam share the step pipeline; beam = rows_per_image > 1 + selection)
+// =============================================================================================
+template <typename ST>
+static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const void* f_rgb,
+                       const void* f_depth, int feat_dtype, int B, int K, bool beam, int start_id,
+                       int end_id, int max_len, const float* u, int64_t* tokens, int32_t* lengths,
+                       float* scores_out, float* alphas_out, float* logits_out, int32_t* back_out,
+                       int32_t* toks_out, float* step_scores_out, float* lse_out, char* ws,
+                       cudaStream_t st) {
+  const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
+  const int is_bf16 = sizeof(ST) == 2;
+  const Pack pk(pack, d, dtype);
+  const DecodeLayout lay(d, dtype, B, K);
+  const long long XW = (long long)lay.XW;
+  const int R = B * K;
+  const int H = d.H, A = d.A, D = d.D, E = d.E, L = d.L, V = d.V;
+  ST* Fsum = reinterpret_cast<ST*>(ws + lay.Fsum);
+  float* meanF = reinterpret_cast<float*>(ws + lay.meanF);
+  ST* att1 = reinterpret_cast<ST*>(ws + lay.att1);
+  ST* XH = reinterpret_cast<ST*>(ws + lay.XH);
+  float* HP = reinterpret_cast<float*>(ws + lay.HP);
+  float* c = reinterpret_cast<float*>(ws + lay.c);
+  float* c_tmp = reinterpret_cast<float*>(ws + lay.c_tmp);
+  ST* h_tmp = reinterpret_cast<ST*>(ws + lay.h_tmp);
+  float* h0 = reinterpret_cast<float*>(ws + lay.h0);
+  float* c0 = reinterpret_cast<float*>(ws + lay.c0);
+  float* gate_part = reinterpret_cast<float*>(ws + lay.gate_part);
+  float* logits_ws = reinterpret_cast<float*>(ws + lay.logits);
+  float* lse_ws = reinterpret_cast<float*>(ws + lay.lse);
+  float* sc[2] = {reinterpret_cast<float*>(ws + lay.scores), reinterpret_cast<float*>(ws + lay.scores2)};
+  uint8_t* fin[2] = {reinterpret_cast<uint8_t*>(ws + lay.fin), reinterpret_cast<uint8_t*>(ws + lay.fin2)};
+  int32_t* back_ws = reinterpret_cast<int32_t*>(ws + lay.back);
+  int32_t* tok_ws = reinterpret_cast<int32_t*>(ws + lay.tok);
+
+  const ST* F = nullptr;
+  DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, att1, &F, st));
+  DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, h0, 0, H, c0, st));
+  DIC_CUDA(cudaMemsetAsync(XH, 0, (size_t)2 * R * XW * sizeof(ST), st));
+  decode_init_kernel<ST><<<cdiv(R * (E + H), 256), 256, 0, st>>>(
+      h0, c0, reinterpret_cast<const ST*>(pk.Emb()), start_id, XH, XW, E + D, c, R, K, E, H);
+  DIC_LAUNCH_CHECK();
+  if (beam) {
+    beam_state_init_kernel<<<cdiv(R, 256), 256, 0, st>>>(sc[0], fin[0], B, K);
+    DIC_LAUNCH_CHECK();
+  }
+
+  for (int t = 0; t < max_len; ++t) {
+    ST* X = XH + (size_t)(t & 1) * R * XW;
+    ST* Xn = XH + (size_t)((t + 1) & 1) * R * XW;
+    DIC_TRY(hproj<ST>(d, pk, X + E + D, XW, R, HP, st));
+
+    AttnFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.F = F; a.att1 = att1; a.hp = HP; a.w_full = pk.w_full(); a.b_full = pk.b_full();
+    a.u = u ? u + (size_t)t * R * L : nullptr;
+    a.alpha_out = alphas_out ? alphas_out + (size_t)t * R * L : nullptr;
+    a.alpha_stride = L;
+    a.z_out = nullptr;
+    a.zg_out = X + E; a.zg_stride = XW;
+    a.L = L; a.D = D; a.A = A; a.mode = attn_mode; a.inv_temp = 1.f;
+    DIC_TRY(launch_attn_step<ST>(a, B, K, st));
+
+    int splits = 1;
+    DIC_TRY(gates_gemm<ST>(d, pk, X, XW, R, R, gate_part, &splits, st));
+
+    LstmFwdArgs l;
+    memset(&l, 0, sizeof(l));
+    l.gate_part = gate_part; l.part_stride = (long long)R * 4 * H; l.splits = splits;
+    l.bias_g = pk.bias_g();
+    l.c_in = c;
+    l.c_out = beam ? c_tmp : c;
+    l.h_out = beam ? h_tmp : Xn + E + D;
+    l.h_stride = beam ? H : XW;
+    l.rows = R; l.H = H;
+    DIC_TRY(launch_lstm_fwd<ST>(l, st));
+
+    float* lg = logits_out ? logits_out + (size_t)t * R * V : logits_ws;
+    const ST* hsrc = beam ? h_tmp : Xn + E + D;
+    GemmArgs g = gemm_args_nt(hsrc, is_bf16, beam ? H : XW, pk.Wout(), is_bf16, H, lg, 0, V, R, V, H, pk.b_out());
+    DIC_TRY(gemm(g, st));
+
+    if (!beam) {
+      argmax_embed_kernel<ST><<<R, 256, 0, st>>>(lg, V, tokens + t, max_len,
+                                                 reinterpret_cast<const ST*>(pk.Emb()), E, Xn, XW);
+      DIC_LAUNCH_CHECK();
+    } else {
+      float* lse_t = lse_out ? lse_out + (size_t)t * R : lse_ws;
+      row_lse_kernel<<<R, 256, 0, st>>>(lg, V, lse_t);
+      DIC_LAUNCH_CHECK();
+      int32_t* back_t = back_ws + (size_t)t * R;
+      int32_t* tok_t = tok_ws + (size_t)t * R;
+      DIC_TRY(launch_beam_topk(sc[t & 1], fin[t & 1], lg, lse_t, B, K, V, end_id, sc[(t + 1) & 1], back_t,
+                               tok_t, fin[(t + 1) & 1], st));
+      beam_reorder_kernel<ST><<<cdiv(R * (E + H), 256), 256, 0, st>>>(
+          h_tmp, c_tmp, back_t, tok_t, reinterpret_cast<const ST*>(pk.Emb()), Xn, XW, E + D, c, R, K, E, H);
+      DIC_LAUNCH_CHECK();
+      if (step_scores_out)
+        DIC_CUDA(cudaMemcpyAsync(step_scores_out + (size_t)t * R, sc[(t + 1) & 1], sizeof(float) * R,
+                                 cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (beam) {
+    beam_backtrack_kernel<<<cdiv(B, 128), 128, 0, st>>>(back_ws, tok_ws, sc[max_len & 1], B, K, max_len,
+                                                        end_id, tokens, lengths, scores_out);
+    DIC_LAUNCH_CHECK();
+    if (back_out)
+      DIC_CUDA(cudaMemcpyAsync(back_out, back_ws, sizeof(int32_t) * (size_t)max_len * R,
+                               cudaMemcpyDeviceToDevice, st));
+    if (toks_out)
+      DIC_CUDA(cudaMemcpyAsync(toks_out, tok_ws, sizeof(int32_t) * (size_t)max_len * R,
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+}  // namespace dic
+
+using namespace dic;
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+int dic_version(void) { return DIC_VERSION; }
+const char* dic_last_error(void) { return g_err; }
+
+size_t dic_pack_bytes(const dic_dims* dims, int dtype) {
+  if (check_dims(dims, dtype)) return 0;
+  return PackLayout(*dims, dtype).bytes;
+}
+
+int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void* pack, void* stream) {
+  DIC_TRY(check_dims(dims, dtype));
+  if (!p || !pack) DIC_FAIL(-1, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dic_dims& d = *dims;
+  const PackLayout lay(d, dtype);
+  char* base = reinterpret_cast<char*>(pack);
+  const int bf = dtype == DIC_BF16;
+  const size_t es = lay.es;
+  const long long XW = (long long)d.E + d.D + d.H;
+  DIC_TRY(launch_copy2d(p->enc_att_w, d.D, base + lay.Wenc, d.D, bf, d.A, d.D, st));
+  DIC_TRY(launch_copy2d(p->w_hh, d.H, base + lay.Whdb, d.H, bf, 4 * d.H, d.H, st));
+  DIC_TRY(launch_copy2d(p->dec_att_w, d.H, base + lay.Whdb + (size_t)4 * d.H * d.H * es, d.H, bf, d.A, d.H, st));
+  DIC_TRY(launch_copy2d(p->fbeta_w, d.H, base + lay.Whdb + (size_t)(4 * d.H + d.A) * d.H * es, d.H, bf, d.D,
+                        d.H, st));
+  DIC_TRY(launch_copy2d(p->w_ih, d.E + d.D, base + lay.Wg, XW, bf, 4 * d.H, d.E + d.D, st));
+  DIC_TRY(launch_copy2d(p->w_hh, d.H, base + lay.Wg + (size_t)(d.E + d.D) * es, XW, bf, 4 * d.H, d.H, st));
+  DIC_TRY(launch_copy2d(p->init_w, d.D, base + lay.Winit, d.D, bf, 2 * d.H, d.D, st));
+  DIC_TRY(launch_copy2d(p->lin_w, d.H, base + lay.Wout, d.H, bf, d.V, d.H, st));
+  DIC_TRY(launch_copy2d(p->embed_w, d.E, base + lay.Emb, d.E, bf, d.V, d.E, st));
+  DIC_TRY(launch_copy2d(p->enc_att_b, d.A, base + lay.b_enc, d.A, 0, 1, d.A, st));
+  DIC_TRY(launch_copy2d(p->dec_att_b, d.A, base + lay.bias_db, d.A, 0, 1, d.A, st));
+  DIC_TRY(launch_copy2d(p->fbeta_b, d.D, base + lay.bias_db + sizeof(float) * d.A, d.D, 0, 1, d.D, st));
+  add_vec_kernel<<<cdiv(4 * d.H, 256), 256, 0, st>>>(p->b_ih, p->b_hh,
+                                                     reinterpret_cast<float*>(base + lay.bias_g), 4 * d.H);
+  DIC_LAUNCH_CHECK();
+  DIC_TRY(launch_copy2d(p->init_b, 2 * d.H, base + lay.b_init, 2 * d.H, 0, 1, 2 * d.H, st));
+  DIC_TRY(launch_copy2d(p->lin_b, d.V, base + lay.b_out, d.V, 0, 1, d.V, st));
+  DIC_TRY(launch_copy2d(p->full_att_w, d.A, base + lay.w_full, d.A, 0, 1, d.A, st));
+  DIC_TRY(launch_copy2d(p->full_att_b, 1, base + lay.b_full, 1, 0, 1, 1, st));
+  return 0;
+}
+
+size_t dic_train_workspace_bytes(const dic_dims* dims, int dtype, int B, int T) {
+  if (check_dims(dims, dtype) || B <= 0 || T <= 0) return 0;
+  return TrainLayout(*dims, dtype, B, T).bytes;
+}
+
+int dic_decoder_forward(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
+                        const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
+                        const int32_t* host_batch_sizes, int T, int B, const float* u, float temp,
+                        const float* dropout_mask, float* logits, float* alphas, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  DIC_TRY(check_dims(dims, dtype));
+  if (!pack || !f_rgb || !captions || !host_batch_sizes || !logits || !alphas || !workspace)
+    DIC_FAIL(-1, "null argument");
+  if (attn_mode < 0 || attn_mode > 2) DIC_FAIL(-1, "bad attn_mode %d", attn_mode);
+  if (attn_mode != DIC_ATTN_SOFT && !u) DIC_FAIL(-1, "hard attention needs the uniform draws u");
+  if (attn_mode == DIC_ATTN_GUMBEL_SOFTMAX && !(temp > 0.f)) DIC_FAIL(-1, "temp must be > 0");
+  StepSizes sizes;
+  int total = 0;
+  DIC_TRY(make_sizes(host_batch_sizes, T, B, &sizes, &total));
+  if (sizes.n[0] != B) DIC_FAIL(-1, "batch_sizes[0]=%d must equal B=%d", sizes.n[0], B);
+  if (T + 1 > cap_stride) DIC_FAIL(-1, "captions has %d columns, need >= T+1 = %d", cap_stride, T + 1);
+  const size_t need = TrainLayout(*dims, dtype, B, T).bytes;
+  if (workspace_bytes < need) DIC_FAIL(-1, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (dtype == DIC_BF16)
+    return decoder_forward_impl<bf16>(*dims, attn_mode, pack, f_rgb, f_depth, feat_dtype, captions, cap_stride,
+                                      sizes, total, T, B, u, temp, dropout_mask, logits, alphas, ws, st);
+  return decoder_forward_impl<float>(*dims, attn_mode, pack, f_rgb, f_depth, feat_dtype, captions, cap_stride,
+                                     sizes, total, T, B, u, temp, dropout_mask, logits, alphas, ws, st);
+}
+
+int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
+                         const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
+                         const int32_t* host_batch_sizes, int T, int B, const float* d_logits,
+                         const float* d_alphas, const float* alphas, float temp, const float* dropout_mask,
+                         const dic_params* grads, float* d_feats, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  DIC_TRY(check_dims(dims, dtype));
+  // same aliasing rule as prologue(): no fused copy was made when there is no depth tensor and
+  // the annotations already have the storage dtype
+  const void* f_alias =
+      (f_depth == nullptr && feat_dtype == dtype) ? f_rgb : nullptr;
+  if (!pack || !f_rgb || !captions || !host_batch_sizes || !d_logits || !alphas || !grads || !workspace)
+    DIC_FAIL(-1, "null argument");
+  StepSizes sizes;
+  int total = 0;
+  DIC_TRY(make_sizes(host_batch_sizes, T, B, &sizes, &total));
+  const size_t need = TrainLayout(*dims, dtype, B, T).bytes;
+  if (workspace_bytes < need) DIC_FAIL(-1, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (dtype == DIC_BF16)
+    return decoder_backward_impl<bf16>(*dims, attn_mode, pack, captions, cap_stride, sizes, total, T, B,
+                                       d_logits, d_alphas, alphas, temp, dropout_mask, *grads, d_feats, f_alias,
+                                       ws, st);
+  return decoder_backward_impl<float>(*dims, attn_mode, pack, captions, cap_stride, sizes, total, T, B, d_logits,
+                                      d_alphas, alphas, temp, dropout_mask, *grads, d_feats, f_alias, ws, st);
+}
+
+size_t dic_decode_workspace_bytes(const dic_dims* dims, int dtype, int B, int beam) {
+  if (check_dims(dims, dtype) || B <= 0 || beam <= 0) return 0;
+  return DecodeLayout(*dims, dtype, B, beam).bytes;
+}
+
+int dic_decode_greedy(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
+                      const void* f_depth, int feat_dtype, int B, int start_id, int max_len, const float* u,
+                      int64_t* tokens, float* alphas_out, float* logits_out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  DIC_TRY(check_dims(dims, dtype));
+  if (!pack || !f_rgb || !tokens || !workspace) DIC_FAIL(-1, "null argument");
+  if (attn_mode != DIC_ATTN_SOFT && attn_mode != DIC_ATTN_GUMBEL_MAX)
+    DIC_FAIL(-1, "greedy decode supports soft and gumbel-max attention");
+  if (attn_mode == DIC_ATTN_GUMBEL_MAX && !u) DIC_FAIL(-1, "gumbel-max needs the uniform draws u");
+  if (B <= 0 || max_len <= 0 || max_len > DIC_MAX_STEPS) DIC_FAIL(-1, "bad B/max_len");
+  if (start_id < 0 || start_id >= dims->V) DIC_FAIL(-1, "start_id out of range");
+  const size_t need = DecodeLayout(*dims, dtype, B, 1).bytes;
+  if (workspace_bytes < need) DIC_FAIL(-1, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (dtype == DIC_BF16)
+    return decode_impl<bf16>(*dims, attn_mode, pack, f_rgb, f_depth, feat_dtype, B, 1, false, start_id, -1,
+                             max_len, u, tokens, nullptr, nullptr, alphas_out, logits_out, nullptr, nullptr,
+                             nullptr, nullptr, ws, st);
+  return decode_impl<float>(*dims, attn_mode, pack, f_rgb, f_depth, feat_dtype, B, 1, false, start_id, -1, max_len,
+                            u, tokens, nullptr, nullptr, alphas_out, logits_out, nullptr, nullptr, nullptr,
+                            nullptr, ws, st);
+}
+
+int dic_decode_beam(const dic_dims* dims, int dtype, const void* pack, const void* f_rgb, const void* f_depth,
+                    int feat_dtype, int B, int beam, int start_id, int end_id, int max_len, int64_t* tokens,
+                    int32_t* lengths, float* scores, int32_t* back, int32_t* toks, float* step_scores,
+                    float* lse, float* logits_out, void* workspace, size_t workspace_bytes, void* stream) {
+  DIC_TRY(check_dims(dims, dtype));
+  if (!pack || !f_rgb || !tokens || !lengths || !scores || !workspace) DIC_FAIL(-1, "null argument");
+  if (beam < 1 || beam > DIC_MAX_BEAM) DIC_FAIL(-1, "beam must be in 1..%d", DIC_MAX_BEAM);
+  if (beam > dims->V) DIC_FAIL(-1, "beam larger than vocabulary");
+  if (B <= 0 || max_len <= 0 || max_len > DIC_MAX_STEPS) DIC_FAIL(-1, "bad B/max_len");
+  if (start_id < 0 || start_id >= dims->V || end_id < 0 || end_id >= dims->V)
+    DIC_FAIL(-1, "start/end id out of range");
+  const size_t need = DecodeLayout(*dims, dtype, B, beam).bytes;
+  if (workspace_bytes < need) DIC_FAIL(-1, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (dtype == DIC_BF16)
+    return decode_impl<bf16>(*dims, DIC_ATTN_SOFT, pack, f_rgb, f_depth, feat_dtype, B, beam, true, start_id,
+                             end_id, max_len, nullptr, tokens, lengths, scores, nullptr, logits_out, back, toks,
+                             step_scores, lse, ws, st);
+  return decode_impl<float>(*dims, DIC_ATTN_SOFT, pack, f_rgb, f_depth, feat_dtype, B, beam, true, start_id,
+                            end_id, max_len, nullptr, tokens, lengths, scores, nullptr, logits_out, back, toks,
+                            step_scores, lse, ws, st);
+}
+
+// ---- standalone attention module -------------------------------------------------------------
+namespace {
+struct AttnWsLayout {
+  size_t Fst, att1, hp, Wenc, Wdec, hst, zg, bias, bytes;
+  int es;
+  AttnWsLayout(const dic_dims& d, int dtype, int B) {
+    es = dtype == DIC_BF16 ? 2 : 4;
+    Carver c;
+    Fst = c.take((size_t)B * d.L * d.D * es);
+    att1 = c.take((size_t)B * d.L * d.A * es);
+    hp = c.take(sizeof(float) * B * (d.A + d.D));
+    Wenc = c.take((size_t)d.A * d.D * es);
+    Wdec = c.take((size_t)d.A * d.H * es);
+    hst = c.take((size_t)B * d.H * es);
+    zg = c.take((size_t)B * d.D * es);
+    bias = c.take(sizeof(float) * 4);
+    bytes = c.off;
+  }
+};
+__global__ void fill_kernel(float* p, float v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = v;
+}
+__global__ void cast_out_kernel(const void* src, int src_bf16, float* dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    dst[i] = ld_as_float(src, i, src_bf16);
+}
+}  // namespace
+
+size_t dic_attention_workspace_bytes(const dic_dims* dims, int dtype, int B) {
+  if (check_dims(dims, dtype) || B <= 0) return 0;
+  return AttnWsLayout(*dims, dtype, B).bytes;
+}
+
+}  // extern "C" (templates need C++ linkage)
+
+template <typename ST>
+static int attention_forward_impl(const dic_dims& d, int attn_mode, const float* enc_w, const float* enc_b,
+                                  const float* dec_w, const float* dec_b, const float* full_w,
+                                  const float* full_b, const float* feats, const float* h, int B,
+                                  const float* u, float temp, float* context, float* alpha, char* ws,
+                                  cudaStream_t st) {
+  const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
+  const int bf = sizeof(ST) == 2;
+  const AttnWsLayout lay(d, dtype, B);
+  ST* Fst = reinterpret_cast<ST*>(ws + lay.Fst);
+  ST* att1 = reinterpret_cast<ST*>(ws + lay.att1);
+  float* hp = reinterpret_cast<float*>(ws + lay.hp);
+  ST* Wenc = reinterpret_cast<ST*>(ws + lay.Wenc);
+  ST* Wdec = reinterpret_cast<ST*>(ws + lay.Wdec);
+  ST* hst = reinterpret_cast<ST*>(ws + lay.hst);
+  ST* zg = reinterpret_cast<ST*>(ws + lay.zg);
+  const ST* F = reinterpret_cast<const ST*>(feats);
+  if (bf) {
+    DIC_TRY(launch_copy2d(feats, d.D, Fst, d.D, 1, B * d.L, d.D, st));
+    F = Fst;
+  }
+  DIC_TRY(launch_copy2d(enc_w, d.D, Wenc, d.D, bf, d.A, d.D, st));
+  DIC_TRY(launch_copy2d(dec_w, d.H, Wdec, d.H, bf, d.A, d.H, st));
+  DIC_TRY(launch_copy2d(h, d.H, hst, d.H, bf, B, d.H, st));
+  GemmArgs g = gemm_args_nt(F, bf, d.D, Wenc, bf, d.D, att1, bf, d.A, B * d.L, d.A, d.D, enc_b);
+  DIC_TRY(gemm(g, st));
+  // hp = [att2 | beta := 1]  (the standalone module has no f_beta gate)
+  fill_kernel<<<148, 256, 0, st>>>(hp, 1.f, (size_t)B * (d.A + d.D));
+  DIC_LAUNCH_CHECK();
+  g = gemm_args_nt(hst, bf, d.H, Wdec, bf, d.H, hp, 0, d.A + d.D, B, d.A, d.H, dec_b);
+  DIC_TRY(gemm_generic(g, st));
+  AttnFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.F = F; a.att1 = att1; a.hp = hp; a.w_full = full_w; a.b_full = full_b; a.u = u;
+  a.alpha_out = alpha; a.alpha_stride = d.L;
+  a.z_out = context;
+  a.zg_out = zg; a.zg_stride = d.D;
+  a.L = d.L; a.D = d.D; a.A = d.A; a.mode = attn_mode;
+  a.inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
+  return launch_attn_step<ST>(a, B, 1, st);
+}
+
+extern "C" {
+
+int dic_attention_forward(const dic_dims* dims, int dtype, int attn_mode, const float* enc_w, const float* enc_b,
+                          const float* dec_w, const float* dec_b, const float* full_w, const float* full_b,
+                          const float* feats, const float* h, int B, const float* u, float temp, float* context,
+                          float* alpha, void* workspace, size_t workspace_bytes, void* stream) {
+  DIC_TRY(check_dims(dims, dtype));
+  if (!enc_w || !enc_b || !dec_w || !dec_b || !full_w || !full_b || !feats || !h || !context || !alpha ||
+      !workspace)
+    DIC_FAIL(-1, "null argument");
+  if (attn_mode != DIC_ATTN_SOFT && !u) DIC_FAIL(-1, "hard attention needs the uniform draws u");
+  if (attn_mode == DIC_ATTN_GUMBEL_SOFTMAX && !(temp > 0.f)) DIC_FAIL(-1, "temp must be > 0");
+  const size_t need = AttnWsLayout(*dims, dtype, B).bytes;
+  if (workspace_bytes < need) DIC_FAIL(-1, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (dtype == DIC_BF16)
+    return attention_forward_impl<bf16>(*dims, attn_mode, enc_w, enc_b, dec_w, dec_b, full_w, full_b, feats, h, B,
+                                        u, temp, context, alpha, ws, st);
+  return attention_forward_impl<float>(*dims, attn_mode, enc_w, enc_b, dec_w, dec_b, full_w, full_b, feats, h, B, u,
+                                       temp, context, alpha, ws, st);
+}
+
+int dic_beam_select(const float* scores, const uint8_t* finished, const float* logits, const float* lse, int B,
+                    int K, int V, int end_id, float* new_scores, int32_t* back, int32_t* tok,
+                    uint8_t* new_finished, void* stream) {
+  if (!scores || !finished || !logits || !lse || !new_scores || !back || !tok || !new_finished)
+    DIC_FAIL(-1, "null argument");
+  return launch_beam_topk(scores, finished, logits, lse, B, K, V, end_id, new_scores, back, tok, new_finished,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dic_row_lse(const float* logits, int R, int V, float* lse, void* stream) {
+  if (!logits || !lse || R <= 0 || V <= 0) DIC_FAIL(-1, "bad argument");
+  row_lse_kernel<<<R, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, V, lse);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+int dic_gemm_nt(int engine, int M, int N, int K, const void* A, int a_dtype, const void* B, int b_dtype,
+                const float* bias, float* C, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) DIC_FAIL(-1, "bad argument");
+  GemmArgs g = gemm_args_nt(A, a_dtype == DIC_BF16, K, B, b_dtype == DIC_BF16, K, C, 0, N, M, N, K, bias);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (engine == 1) {
+    if (!tc_gemm_eligible(g)) DIC_FAIL(-5, "shape/dtype not eligible for the tcgen05 engine");
+    return tc_gemm(g, st);
+  }
+  return gemm_generic(g, st);
+}
+
+}  // extern "C"

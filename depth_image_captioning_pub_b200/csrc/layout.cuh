@@ -1,0 +1,150 @@
+// Host-side memory plans: the packed-weight block and the training / decode workspaces.
+// Everything lives in caller-provided device memory; these structs only compute offsets.
+#pragma once
+#include "common.cuh"
+
+namespace dic {
+
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+// Compute-layout weights.  ST = storage dtype of the mode (fp32 or bf16).
+//   Wenc  [A,D]            attention.encoder_att.weight
+//   Whdb  [4H+A+D, H]      rows: W_hh | W_dec | W_beta  (backward: dh = G . Whdb)
+//         Wdb = Whdb + 4H*H  -> [A+D, H] forward h-projection (att2 | beta)
+//   Wg    [4H, E+D+H]      [W_ih | W_hh]: gates = [emb|zg|h] . Wg^T
+//   Winit [2H,D], Wout [V,H], Emb [V,E]
+//   fp32: b_enc[A], bias_db[A+D] = b_dec|b_beta, bias_g[4H] = b_ih+b_hh, b_init[2H], b_out[V],
+//         w_full[A], b_full[1]
+struct PackLayout {
+  size_t Wenc, Whdb, Wg, Winit, Wout, Emb;
+  size_t b_enc, bias_db, bias_g, b_init, b_out, w_full, b_full;
+  size_t bytes;
+  int es;  // element size of ST
+  PackLayout(const dic_dims& d, int dtype) {
+    es = dtype == DIC_BF16 ? 2 : 4;
+    Carver c;
+    const size_t XW = (size_t)d.E + d.D + d.H;
+    Wenc = c.take((size_t)d.A * d.D * es);
+    Whdb = c.take((size_t)(4 * d.H + d.A + d.D) * d.H * es);
+    Wg = c.take((size_t)4 * d.H * XW * es);
+    Winit = c.take((size_t)2 * d.H * d.D * es);
+    Wout = c.take((size_t)d.V * d.H * es);
+    Emb = c.take((size_t)d.V * d.E * es);
+    b_enc = c.take(sizeof(float) * d.A);
+    bias_db = c.take(sizeof(float) * (d.A + d.D));
+    bias_g = c.take(sizeof(float) * 4 * d.H);
+    b_init = c.take(sizeof(float) * 2 * d.H);
+    b_out = c.take(sizeof(float) * d.V);
+    w_full = c.take(sizeof(float) * d.A);
+    b_full = c.take(sizeof(float) * 4);
+    bytes = c.off;
+  }
+};
+
+// Views into a packed-weight block.
+struct Pack {
+  const char* base;
+  PackLayout lay;
+  Pack(const void* p, const dic_dims& d, int dtype) : base(reinterpret_cast<const char*>(p)), lay(d, dtype) {}
+  const void* Wenc() const { return base + lay.Wenc; }
+  const void* Whdb() const { return base + lay.Whdb; }
+  const void* Wdb(const dic_dims& d) const { return base + lay.Whdb + (size_t)4 * d.H * d.H * lay.es; }
+  const void* Wg() const { return base + lay.Wg; }
+  const void* Winit() const { return base + lay.Winit; }
+  const void* Wout() const { return base + lay.Wout; }
+  const void* Emb() const { return base + lay.Emb; }
+  const float* b_enc() const { return reinterpret_cast<const float*>(base + lay.b_enc); }
+  const float* bias_db() const { return reinterpret_cast<const float*>(base + lay.bias_db); }
+  const float* bias_g() const { return reinterpret_cast<const float*>(base + lay.bias_g); }
+  const float* b_init() const { return reinterpret_cast<const float*>(base + lay.b_init); }
+  const float* b_out() const { return reinterpret_cast<const float*>(base + lay.b_out); }
+  const float* w_full() const { return reinterpret_cast<const float*>(base + lay.w_full); }
+  const float* b_full() const { return reinterpret_cast<const float*>(base + lay.b_full); }
+};
+
+constexpr int kGateSplitsMax = 16;
+
+// Training workspace (forward state saved for backward + backward scratch).
+struct TrainLayout {
+  size_t Fsum, meanF, att1, XH, HP, Z, acts, c_all, gate_part, Hdrop;
+  size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec;
+  size_t bytes;
+  size_t XW, GW;
+  int es;
+  TrainLayout(const dic_dims& d, int dtype, int B, int T) {
+    es = dtype == DIC_BF16 ? 2 : 4;
+    XW = (size_t)d.E + d.D + d.H;
+    GW = (size_t)4 * d.H + d.A + d.D;
+    const size_t TB = (size_t)T * B;
+    Carver c;
+    Fsum = c.take((size_t)B * d.L * d.D * es);
+    meanF = c.take(sizeof(float) * B * d.D);
+    att1 = c.take((size_t)B * d.L * d.A * es);
+    XH = c.take((TB + B) * XW * es);
+    HP = c.take(sizeof(float) * TB * (d.A + d.D));
+    Z = c.take(sizeof(float) * TB * d.D);
+    acts = c.take(sizeof(float) * TB * 4 * d.H);
+    c_all = c.take(sizeof(float) * (TB + B) * d.H);
+    gate_part = c.take(sizeof(float) * kGateSplitsMax * B * 4 * d.H);
+    Hdrop = c.take(TB * d.H * es);
+    G = c.take(TB * GW * es);
+    DZ = c.take(TB * d.D * es);
+    de = c.take(sizeof(float) * TB * d.L);
+    dzg = c.take(sizeof(float) * B * d.D);
+    dh = c.take(sizeof(float) * B * d.H);
+    dc = c.take(sizeof(float) * B * d.H);
+    dHout = c.take(sizeof(float) * TB * d.H);
+    dwfull_part = c.take(sizeof(float) * TB * d.A);
+    dbfull_part = c.take(sizeof(float) * TB);
+    datt1 = c.take((size_t)B * d.L * d.A * es);
+    dXemb = c.take(sizeof(float) * TB * d.E);
+    dmeanF = c.take(sizeof(float) * B * d.D);
+    tmpvec = c.take(sizeof(float) * (GW + 16));
+    bytes = c.off;
+  }
+};
+
+// Decode workspace: R = B*beam rows.
+struct DecodeLayout {
+  size_t Fsum, meanF, att1, XH, HP, c, c_tmp, h_tmp, h0, c0, gate_part, logits, lse;
+  size_t scores, scores2, fin, fin2, back, tok, step_scores;
+  size_t bytes;
+  size_t XW;
+  int es;
+  DecodeLayout(const dic_dims& d, int dtype, int B, int beam, int max_len = DIC_MAX_STEPS) {
+    es = dtype == DIC_BF16 ? 2 : 4;
+    XW = (size_t)d.E + d.D + d.H;
+    const size_t R = (size_t)B * beam;
+    Carver c_;
+    Fsum = c_.take((size_t)B * d.L * d.D * es);
+    meanF = c_.take(sizeof(float) * B * d.D);
+    att1 = c_.take((size_t)B * d.L * d.A * es);
+    XH = c_.take(2 * R * XW * es);
+    HP = c_.take(sizeof(float) * R * (d.A + d.D));
+    c = c_.take(sizeof(float) * R * d.H);
+    c_tmp = c_.take(sizeof(float) * R * d.H);
+    h_tmp = c_.take(R * d.H * es);
+    h0 = c_.take(sizeof(float) * B * d.H);
+    c0 = c_.take(sizeof(float) * B * d.H);
+    gate_part = c_.take(sizeof(float) * kGateSplitsMax * R * 4 * d.H);
+    logits = c_.take(sizeof(float) * R * d.V);
+    lse = c_.take(sizeof(float) * R);
+    scores = c_.take(sizeof(float) * R);
+    scores2 = c_.take(sizeof(float) * R);
+    fin = c_.take(R);
+    fin2 = c_.take(R);
+    back = c_.take(sizeof(int32_t) * R * max_len);
+    tok = c_.take(sizeof(int32_t) * R * max_len);
+    step_scores = c_.take(sizeof(float) * R * max_len);
+    bytes = c_.off;
+  }
+};
+
+}  // namespace dic

@@ -1,0 +1,111 @@
+// LSTM cell pointwise kernels (torch.nn.LSTMCell semantics, gate order i,f,g,o;
+// depth_models.py:122,193).  The gate pre-activations come from the [emb|zg|h] x [W_ih|W_hh]^T
+// GEMM as split-K partial tiles; this kernel reduces them, adds b_ih+b_hh, applies the
+// nonlinearities and writes h' directly where the next step's GEMMs read it.
+#pragma once
+#include "common.cuh"
+
+namespace dic {
+
+struct LstmFwdArgs {
+  const float* gate_part;  // [splits][rows_alloc][4H] fp32
+  long long part_stride;   // elements between partials
+  int splits;
+  const float* bias_g;     // [4H] = b_ih + b_hh
+  const float* c_in;       // [rows, H]
+  float* c_out;            // [rows, H]
+  float* acts;             // [rows, 4H] post-activation i,f,g,o (saved for backward) or null
+  void* h_out;             // ST, row r at h_out + r*h_stride
+  long long h_stride;
+  void* hdrop_out;         // ST [rows, H] = h * mask (logits GEMM operand) or null
+  const float* mask;       // [rows, H] or null
+  float* h_f32_out;        // optional fp32 copy [rows, H] or null
+  int rows, H;
+};
+
+template <typename ST>
+__global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.rows * p.H) return;
+  const int r = idx / p.H, j = idx - r * p.H;
+  const int H = p.H;
+  float g4[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float s = p.bias_g[q * H + j];
+    for (int sp = 0; sp < p.splits; ++sp)
+      s += p.gate_part[(size_t)sp * p.part_stride + (size_t)r * 4 * H + q * H + j];
+    g4[q] = s;
+  }
+  const float ig = sigmoidf_acc(g4[0]);
+  const float fg = sigmoidf_acc(g4[1]);
+  const float gg = tanhf(g4[2]);
+  const float og = sigmoidf_acc(g4[3]);
+  const float c = fg * p.c_in[idx] + ig * gg;
+  const float h = og * tanhf(c);
+  p.c_out[idx] = c;
+  if (p.acts) {
+    float* a = p.acts + (size_t)r * 4 * H;
+    a[j] = ig; a[H + j] = fg; a[2 * H + j] = gg; a[3 * H + j] = og;
+  }
+  reinterpret_cast<ST*>(p.h_out)[(size_t)r * p.h_stride + j] = from_f<ST>(h);
+  if (p.h_f32_out) p.h_f32_out[idx] = h;
+  if (p.hdrop_out) {
+    const float m = p.mask ? p.mask[idx] : 1.f;
+    reinterpret_cast<ST*>(p.hdrop_out)[idx] = from_f<ST>(h * m);
+  }
+}
+
+template <typename ST>
+inline int launch_lstm_fwd(const LstmFwdArgs& p, cudaStream_t st) {
+  if (p.rows <= 0) return 0;
+  lstm_fwd_kernel<ST><<<cdiv(p.rows * p.H, 256), 256, 0, st>>>(p);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward through the cell for the first `rows` (valid) batch rows of one step.
+struct LstmBwdArgs {
+  const float* dh_carry;  // [B,H] from step t+1 (W_hh, f_beta, decoder_att paths)
+  const float* dh_out;    // [rows,H] d(logits).W_out for this step's packed rows
+  const float* mask;      // [rows,H] dropout mask or null
+  float* dc_carry;        // [B,H] in/out
+  const float* acts;      // [rows,4H]
+  const float* c_new;     // [rows,H]
+  const float* c_prev;    // [rows,H]
+  void* G;                // ST, row r at G + r*g_stride, columns [0,4H) = d(pre-activations)
+  long long g_stride;
+  int rows, H;
+};
+
+template <typename ST>
+__global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.rows * p.H) return;
+  const int r = idx / p.H, j = idx - r * p.H;
+  const int H = p.H;
+  const float* a = p.acts + (size_t)r * 4 * H;
+  const float ig = a[j], fg = a[H + j], gg = a[2 * H + j], og = a[3 * H + j];
+  const float m = p.mask ? p.mask[idx] : 1.f;
+  const float dh = p.dh_carry[idx] + p.dh_out[idx] * m;
+  const float tc = tanhf(p.c_new[idx]);
+  const float dc = p.dc_carry[idx] + dh * og * (1.f - tc * tc);
+  const float d_o = dh * tc;
+  const float d_i = dc * gg, d_g = dc * ig, d_f = dc * p.c_prev[idx];
+  p.dc_carry[idx] = dc * fg;
+  ST* G = reinterpret_cast<ST*>(p.G) + (size_t)r * p.g_stride;
+  G[j] = from_f<ST>(d_i * ig * (1.f - ig));
+  G[H + j] = from_f<ST>(d_f * fg * (1.f - fg));
+  G[2 * H + j] = from_f<ST>(d_g * (1.f - gg * gg));
+  G[3 * H + j] = from_f<ST>(d_o * og * (1.f - og));
+}
+
+template <typename ST>
+inline int launch_lstm_bwd(const LstmBwdArgs& p, cudaStream_t st) {
+  if (p.rows <= 0) return 0;
+  lstm_bwd_kernel<ST><<<cdiv(p.rows * p.H, 256), 256, 0, st>>>(p);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dic

@@ -1,0 +1,172 @@
+// Memory-bound helpers: RGB+depth fusion, embedding gather/scatter, column sums, weight packing.
+#pragma once
+#include "common.cuh"
+
+namespace dic {
+
+// ---- K0a: Fsum = F_rgb (+ F_depth), mean over L ------------------------------------------------
+// features.add(depth_features) and features.mean(dim=1) (depth_models.py:163,166) in one pass.
+// Grid (D chunks of 1024 columns, B); each thread owns 4 columns and walks the L rows.
+template <typename TIN, typename ST>
+__global__ void __launch_bounds__(256) fuse_feats_kernel(const TIN* __restrict__ rgb,
+                                                         const TIN* __restrict__ dep, ST* __restrict__ fsum,
+                                                         float* __restrict__ meanF, int L, int D) {
+  const int b = blockIdx.y;
+  const int d = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (d >= D) return;
+  const size_t base = (size_t)b * L * D + d;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int l = 0; l < L; ++l) {
+    float v[4];
+    const size_t o = base + (size_t)l * D;
+    if (sizeof(TIN) == 4) {
+      float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rgb) + o);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      if (dep) {
+        float4 c = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dep) + o);
+        v[0] += c.x; v[1] += c.y; v[2] += c.z; v[3] += c.w;
+      }
+    } else {
+      uint2 a = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(rgb) + o);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+      float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+      v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+      if (dep) {
+        uint2 c = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dep) + o);
+        const __nv_bfloat162* g = reinterpret_cast<const __nv_bfloat162*>(&c);
+        float2 g0 = __bfloat1622float2(g[0]), g1 = __bfloat1622float2(g[1]);
+        v[0] += g0.x; v[1] += g0.y; v[2] += g1.x; v[3] += g1.y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] += v[q];
+    if (fsum) {
+      if (sizeof(ST) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(fsum) + o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        uint2 r;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+        h[0] = __floats2bfloat162_rn(v[0], v[1]);
+        h[1] = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(fsum) + o) = r;
+      }
+    }
+  }
+  const float inv = 1.f / (float)L;
+  *reinterpret_cast<float4*>(meanF + (size_t)b * D + d) =
+      make_float4(s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv);
+}
+
+// fsum == nullptr -> only the mean is produced (the caller aliases Fsum to the input).
+template <typename ST>
+inline int launch_fuse_feats(const void* rgb, const void* dep, int feat_bf16, ST* fsum, float* meanF,
+                             int B, int L, int D, cudaStream_t st) {
+  dim3 grid(cdiv(D, 1024), B);
+  if (feat_bf16)
+    fuse_feats_kernel<bf16, ST><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(rgb),
+                                                     reinterpret_cast<const bf16*>(dep), fsum, meanF, L, D);
+  else
+    fuse_feats_kernel<float, ST><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(rgb),
+                                                      reinterpret_cast<const float*>(dep), fsum, meanF, L, D);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- column sums: dst[c] = sum_r src[r*ld + c] (bias gradients) ---------------------------------
+// Grid (column tiles of 32, row chunks); partial sums meet in dst through atomicAdd, so dst
+// must be zeroed first (launcher does it).
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ src, int src_bf16, int R,
+                                                     int C, long long ld, int rows_per_block,
+                                                     float* __restrict__ dst) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (int r = r0 + ry; r < r1; r += 8) s += ld_as_float(src, (size_t)r * ld + c, src_bf16);
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    atomicAdd(dst + c, t);
+  }
+}
+
+inline int launch_colsum(const void* src, int src_bf16, int R, int C, long long ld, float* dst,
+                         cudaStream_t st) {
+  DIC_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * C, st));
+  if (R <= 0 || C <= 0) return 0;
+  int chunks = cdiv(R, 256);
+  if (chunks > 1024) chunks = 1024;
+  const int rpb = cdiv(R, chunks);
+  dim3 grid(cdiv(C, 32), cdiv(R, rpb));
+  colsum_kernel<<<grid, 256, 0, st>>>(src, src_bf16, R, C, ld, rpb, dst);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- embedding gather for teacher forcing: X[t][b][0:E] = Emb[captions[b,t]] (depth_models.py:160)
+template <typename ST>
+__global__ void __launch_bounds__(256) embed_gather_tf_kernel(const ST* __restrict__ emb,
+                                                              const int64_t* __restrict__ captions,
+                                                              int cap_stride, ST* __restrict__ X,
+                                                              long long x_row, long long x_step, int B,
+                                                              int E, int V, StepSizes sizes, int T) {
+  const int t = blockIdx.y;
+  const int n = sizes.n[t];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n * E; i += gridDim.x * 256) {
+    const int b = i / E, e = i - b * E;
+    long long tok = captions[(size_t)b * cap_stride + t];
+    if (tok < 0 || tok >= V) tok = 0;  // out-of-range ids are a caller bug; stay in bounds
+    X[(size_t)t * x_step + (size_t)b * x_row + e] = emb[(size_t)tok * E + e];
+  }
+}
+
+// ---- embedding gradient: dEmb[captions[b,t]] += dX[t][b]  (dEmb zeroed by the caller) -------------
+__global__ void __launch_bounds__(256) embed_scatter_add_kernel(const float* __restrict__ dX,
+                                                                const int64_t* __restrict__ captions,
+                                                                int cap_stride, float* __restrict__ dEmb,
+                                                                int B, int E, int V, StepSizes sizes,
+                                                                int T) {
+  const int t = blockIdx.y;
+  const int n = sizes.n[t];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n * E; i += gridDim.x * 256) {
+    const int b = i / E, e = i - b * E;
+    const long long tok = captions[(size_t)b * cap_stride + t];
+    if (tok < 0 || tok >= V) continue;
+    atomicAdd(dEmb + (size_t)tok * E + e, dX[((size_t)t * B + b) * E + e]);
+  }
+}
+
+// ---- 2-D strided copy with dtype conversion (weight packing) ------------------------------------
+__global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, long long src_ld,
+                                                     void* __restrict__ dst, long long dst_ld,
+                                                     int dst_bf16, int R, int C) {
+  const size_t n = (size_t)R * C;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const size_t r = i / C, c = i - r * C;
+    st_from_float(dst, r * dst_ld + c, src[r * src_ld + c], dst_bf16);
+  }
+}
+
+inline int launch_copy2d(const float* src, long long src_ld, void* dst, long long dst_ld, int dst_bf16,
+                         int R, int C, cudaStream_t st) {
+  const size_t n = (size_t)R * C;
+  if (n == 0) return 0;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  copy2d_kernel<<<blocks, 256, 0, st>>>(src, src_ld, dst, dst_ld, dst_bf16, R, C);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) add_vec_kernel(const float* a, const float* b, float* dst, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = a[i] + b[i];
+}
+
+}  // namespace dic

@@ -1,0 +1,221 @@
+"""Host-side engine: device buffers, weight packing and the autograd bridge to libdic.so.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every
+arithmetic step of the decoder path runs in the CUDA library behind include/dic.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DicError, Dims, Params, PARAM_FIELDS
+
+PRECISIONS = {"fp32": _lib.DIC_F32, "float32": _lib.DIC_F32, "bf16": _lib.DIC_BF16, "bfloat16": _lib.DIC_BF16}
+
+
+def batch_sizes_from_lengths(lengths: Sequence[int]) -> List[int]:
+    """bs_valid per decoder step for caption lengths (incl. <start>) sorted descending
+    (depth_models.py:170,182; util.py:95)."""
+    dec = [int(l) - 1 for l in lengths]
+    if not dec or min(dec) < 1:
+        raise ValueError("every caption needs at least <start> and one target token")
+    if any(dec[i] < dec[i + 1] for i in range(len(dec) - 1)):
+        raise ValueError("lengths must be sorted in descending order (as collate_func does)")
+    return [sum(1 for l in dec if l > t) for t in range(max(dec))]
+
+
+def _params_struct(tensors: Sequence[torch.Tensor]) -> Params:
+    p = Params()
+    for name, t in zip(PARAM_FIELDS, tensors):
+        if t.dtype != torch.float32:
+            raise DicError(f"parameter {name} must be float32, got {t.dtype}")
+        setattr(p, name, _lib.ptr(t))
+    return p
+
+
+class Engine:
+    """Per-(dims, precision, device) state: packed weights and reusable workspaces."""
+
+    def __init__(self, L: int, D: int, A: int, E: int, H: int, V: int, precision: str, device: torch.device):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        if device.type != "cuda":
+            raise DicError("the decoder path runs on CUDA only (no CPU fallback)")
+        self.lib = _lib.load()
+        self.dims = Dims(L, D, A, E, H, V)
+        self.dtype = PRECISIONS[precision]
+        self.device = device
+        nbytes = self.lib.dic_pack_bytes(C.byref(self.dims), self.dtype)
+        if nbytes == 0:
+            raise DicError(self.lib.dic_last_error().decode())
+        self.pack = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self._pack_key = None
+        self._ws: Dict[Tuple, torch.Tensor] = {}
+
+    # ---- weights -------------------------------------------------------------------------
+    def ensure_packed(self, params: Sequence[torch.Tensor]) -> None:
+        """(Re)build the compute-layout weight pack when any parameter changed."""
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key == self._pack_key:
+            return
+        with torch.cuda.device(self.device):
+            ps = _params_struct([p.detach().contiguous() for p in params])
+            _lib.check(self.lib.dic_pack_weights(C.byref(self.dims), self.dtype, C.byref(ps),
+                                                 _lib.ptr(self.pack), _lib.stream_ptr(self.device)))
+        self._pack_key = key
+
+    # ---- workspaces ------------------------------------------------------------------------
+    def train_workspace(self, B: int, T: int, fresh: bool) -> torch.Tensor:
+        n = self.lib.dic_train_workspace_bytes(C.byref(self.dims), self.dtype, B, T)
+        if n == 0:
+            raise DicError(self.lib.dic_last_error().decode())
+        if fresh:   # lives until the matching backward; never shared between graphs
+            return torch.empty(n, dtype=torch.uint8, device=self.device)
+        return self._cached(("train", B, T), n)
+
+    def decode_workspace(self, B: int, beam: int) -> torch.Tensor:
+        n = self.lib.dic_decode_workspace_bytes(C.byref(self.dims), self.dtype, B, beam)
+        if n == 0:
+            raise DicError(self.lib.dic_last_error().decode())
+        return self._cached(("decode", B, beam), n)
+
+    def _cached(self, key, n):
+        t = self._ws.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+    # ---- raw calls ---------------------------------------------------------------------------
+    def forward(self, attn_mode: int, f_rgb, f_depth, captions, batch_sizes: Sequence[int], u, temp: float,
+                dropout_mask, ws) -> Tuple[torch.Tensor, torch.Tensor]:
+        d = self.dims
+        B, T = f_rgb.shape[0], len(batch_sizes)
+        total = int(sum(batch_sizes))
+        logits = torch.empty(total, d.V, dtype=torch.float32, device=self.device)
+        alphas = torch.zeros(B, T, d.L, dtype=torch.float32, device=self.device)
+        bs = (C.c_int32 * T)(*batch_sizes)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dic_decoder_forward(
+                C.byref(d), self.dtype, attn_mode, _lib.ptr(self.pack), _lib.ptr(f_rgb), _lib.ptr(f_depth),
+                _lib.dtype_code(f_rgb), _lib.ptr(captions), captions.shape[1], bs, T, B, _lib.ptr(u),
+                float(temp), _lib.ptr(dropout_mask), _lib.ptr(logits), _lib.ptr(alphas), _lib.ptr(ws),
+                ws.numel(), _lib.stream_ptr(self.device)))
+        return logits, alphas
+
+    def backward(self, attn_mode: int, f_rgb, f_depth, captions, batch_sizes, d_logits, d_alphas, alphas,
+                 temp, dropout_mask, ws, param_shapes, need_dfeat: bool):
+        d = self.dims
+        B, T = f_rgb.shape[0], len(batch_sizes)
+        grads = [torch.empty(s, dtype=torch.float32, device=self.device) for s in param_shapes]
+        d_feats = torch.empty(B, d.L, d.D, dtype=torch.float32, device=self.device) if need_dfeat else None
+        gs = _params_struct(grads)
+        bs = (C.c_int32 * T)(*batch_sizes)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dic_decoder_backward(
+                C.byref(d), self.dtype, attn_mode, _lib.ptr(self.pack), _lib.ptr(f_rgb), _lib.ptr(f_depth),
+                _lib.dtype_code(f_rgb), _lib.ptr(captions), captions.shape[1], bs, T, B, _lib.ptr(d_logits),
+                _lib.ptr(d_alphas), _lib.ptr(alphas), float(temp), _lib.ptr(dropout_mask), C.byref(gs),
+                _lib.ptr(d_feats), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)))
+        return grads, d_feats
+
+    def greedy(self, attn_mode: int, f_rgb, f_depth, start_id: int, max_len: int, u=None,
+               want_alphas: bool = False, want_logits: bool = False):
+        d = self.dims
+        B = f_rgb.shape[0]
+        tokens = torch.empty(B, max_len, dtype=torch.int64, device=self.device)
+        alphas = torch.empty(max_len, B, d.L, dtype=torch.float32, device=self.device) if want_alphas else None
+        logits = torch.empty(max_len, B, d.V, dtype=torch.float32, device=self.device) if want_logits else None
+        ws = self.decode_workspace(B, 1)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dic_decode_greedy(
+                C.byref(d), self.dtype, attn_mode, _lib.ptr(self.pack), _lib.ptr(f_rgb), _lib.ptr(f_depth),
+                _lib.dtype_code(f_rgb), B, int(start_id), int(max_len), _lib.ptr(u), _lib.ptr(tokens),
+                _lib.ptr(alphas), _lib.ptr(logits), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)))
+        return tokens, alphas, logits
+
+    def beam(self, f_rgb, f_depth, start_id: int, end_id: int, beam: int, max_len: int, trace: bool = False,
+             want_logits: bool = False):
+        d = self.dims
+        B = f_rgb.shape[0]
+        dev = self.device
+        tokens = torch.empty(B, max_len, dtype=torch.int64, device=dev)
+        lengths = torch.empty(B, dtype=torch.int32, device=dev)
+        scores = torch.empty(B, dtype=torch.float32, device=dev)
+        back = toks = step_scores = lse = logits = None
+        if trace:
+            back = torch.empty(max_len, B, beam, dtype=torch.int32, device=dev)
+            toks = torch.empty(max_len, B, beam, dtype=torch.int32, device=dev)
+            step_scores = torch.empty(max_len, B, beam, dtype=torch.float32, device=dev)
+            lse = torch.empty(max_len, B, beam, dtype=torch.float32, device=dev)
+        if want_logits:
+            logits = torch.empty(max_len, B * beam, d.V, dtype=torch.float32, device=dev)
+        ws = self.decode_workspace(B, beam)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.dic_decode_beam(
+                C.byref(d), self.dtype, _lib.ptr(self.pack), _lib.ptr(f_rgb), _lib.ptr(f_depth),
+                _lib.dtype_code(f_rgb), B, int(beam), int(start_id), int(end_id), int(max_len), _lib.ptr(tokens),
+                _lib.ptr(lengths), _lib.ptr(scores), _lib.ptr(back), _lib.ptr(toks), _lib.ptr(step_scores),
+                _lib.ptr(lse), _lib.ptr(logits), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        out = dict(tokens=tokens, lengths=lengths, scores=scores)
+        if trace:
+            out.update(back=back, toks=toks, all_scores=step_scores, lse=lse)
+        if want_logits:
+            out["logits"] = logits
+        return out
+
+
+class DecoderFunction(torch.autograd.Function):
+    """Teacher-forced decoder forward/backward through dic_decoder_forward / _backward.
+
+    Inputs: engine, attn_mode, captions, batch_sizes, u, temp, dropout_mask, f_rgb, f_depth, *17 params.
+    Outputs: packed logits [sum(bs), V], alphas [B, T, L].
+    """
+
+    @staticmethod
+    def forward(ctx, engine: Engine, attn_mode: int, captions, batch_sizes, u, temp, dropout_mask, f_rgb,
+                f_depth, *params):
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in params) or f_rgb.requires_grad
+            or (f_depth is not None and f_depth.requires_grad))
+        engine.ensure_packed(params)
+        ws = engine.train_workspace(f_rgb.shape[0], len(batch_sizes), fresh=needs_grad)
+        logits, alphas = engine.forward(attn_mode, f_rgb, f_depth, captions, batch_sizes, u, temp,
+                                        dropout_mask, ws)
+        ctx.engine, ctx.attn_mode, ctx.batch_sizes, ctx.temp = engine, attn_mode, list(batch_sizes), temp
+        ctx.ws = ws
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        ctx.pack_key = engine._pack_key
+        ctx.has_depth = f_depth is not None
+        saved = [captions, f_rgb, alphas]
+        for opt in (f_depth, u, dropout_mask):
+            saved.append(opt if opt is not None else torch.empty(0, device=f_rgb.device))
+        ctx.save_for_backward(*saved)
+        return logits, alphas
+
+    @staticmethod
+    def backward(ctx, d_logits, d_alphas):
+        engine: Engine = ctx.engine
+        if engine._pack_key != ctx.pack_key:
+            raise DicError("parameters were modified between forward and backward")
+        captions, f_rgb, alphas, f_depth, u, dropout_mask = ctx.saved_tensors
+        f_depth = f_depth if ctx.has_depth else None
+        dropout_mask = dropout_mask if dropout_mask.numel() else None
+        if d_logits is None:
+            d_logits = torch.zeros(sum(ctx.batch_sizes), engine.dims.V, dtype=torch.float32, device=f_rgb.device)
+        d_logits = d_logits.contiguous().float()
+        if d_alphas is not None:
+            d_alphas = d_alphas.contiguous().float()
+        need_dfeat = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
+        grads, d_feats = engine.backward(ctx.attn_mode, f_rgb, f_depth, captions, ctx.batch_sizes, d_logits,
+                                         d_alphas, alphas, ctx.temp, dropout_mask, ctx.ws, ctx.param_shapes,
+                                         need_dfeat)
+        ctx.ws = None
+        d_rgb = d_feats.to(f_rgb.dtype) if (ctx.needs_input_grad[7] and d_feats is not None) else None
+        d_dep = None
+        if ctx.has_depth and ctx.needs_input_grad[8] and d_feats is not None:
+            d_dep = d_feats.to(f_depth.dtype)
+        return (None, None, None, None, None, None, None, d_rgb, d_dep, *grads)

@@ -1,0 +1,197 @@
+/*
+ * dic.h -- C ABI of the B200-native (sm_100a) depth-image-captioning decoder path.
+ *
+ * The reference (Kyo-suke-S/Depth_image_captioning_pub) is pure Python/PyTorch and has
+ * no FFI layer; the drop-in boundary is its nn.Module surface.  This
+ * header is the layer BELOW that surface: the host-side Python modules in
+ * depth_image_captioning_pub_b200/ keep the reference's class names, constructor
+ * arguments, state_dict keys and forward/sample/batch_sample signatures and call these
+ * entry points through ctypes.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference checkout, Captioning_models/...).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller (torch tensor.data_ptr())
+ *     unless its name starts with host_;
+ *   - the caller allocates all outputs and the workspace (dic_*_workspace_bytes);
+ *     the library never allocates device memory, never frees, never synchronises;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, negative = error; dic_last_error() gives a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Storage modes (dic_dtype): DIC_F32 keeps annotations, projections and GEMM operands in
+ * fp32 (CUDA-core FMA GEMMs, the parity mode: logits within 1e-4, alpha within 1e-5 of the
+ * reference); DIC_BF16 stores annotations / att1 / GEMM operands in bf16 with fp32
+ * accumulation and fp32 recurrent state (tcgen05 tensor-core GEMMs; logits within 2e-2).
+ */
+#ifndef DIC_H_
+#define DIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIC_VERSION 100
+
+enum dic_dtype { DIC_F32 = 0, DIC_BF16 = 1 };
+
+/* attention variants (attention.py) */
+enum dic_attn_mode {
+  DIC_ATTN_SOFT = 0,           /* Soft_Attention.forward            attention.py:81-95   */
+  DIC_ATTN_GUMBEL_SOFTMAX = 1, /* Hard_Attention.forward            attention.py:132-148 */
+  DIC_ATTN_GUMBEL_MAX = 2      /* Hard_Attention.Hard_sample        attention.py:150-167 */
+};
+
+#define DIC_MAX_STEPS 128 /* longest decoder sequence (reference: max_length 30) */
+#define DIC_MAX_BEAM 8
+
+/* Problem dimensions (config.py:11-15 defaults: L=196 D=2048 A=E=H=128).
+ * Constraints: D % 8 == 0, A % 4 == 0, E % 4 == 0, H % 4 == 0, A <= 1024, L <= 1024. */
+typedef struct dic_dims {
+  int32_t L; /* annotation vectors per image (14*14)        */
+  int32_t D; /* annotation channels        dim_encoder      */
+  int32_t A; /* attention dim              dim_attention    */
+  int32_t E; /* embedding dim              dim_embedding    */
+  int32_t H; /* LSTM hidden dim            dim_decoder      */
+  int32_t V; /* vocabulary size                              */
+} dic_dims;
+
+/* The 17 fp32 parameter tensors of a reference decoder, in state_dict layout
+ * (depth_models.py:106-135; identical for soft/hard and base/depth decoders). */
+typedef struct dic_params {
+  float* enc_att_w;  /* attention.encoder_att.weight [A,D]   */
+  float* enc_att_b;  /* attention.encoder_att.bias   [A]     */
+  float* dec_att_w;  /* attention.decoder_att.weight [A,H]   */
+  float* dec_att_b;  /* attention.decoder_att.bias   [A]     */
+  float* full_att_w; /* attention.full_att.weight    [1,A]   */
+  float* full_att_b; /* attention.full_att.bias      [1]     */
+  float* embed_w;    /* embed.weight                 [V,E]   */
+  float* w_ih;       /* decode_step.weight_ih        [4H,E+D] gate order i,f,g,o */
+  float* w_hh;       /* decode_step.weight_hh        [4H,H]  */
+  float* b_ih;       /* decode_step.bias_ih          [4H]    */
+  float* b_hh;       /* decode_step.bias_hh          [4H]    */
+  float* init_w;     /* init_linear.weight           [2H,D]  */
+  float* init_b;     /* init_linear.bias             [2H]    */
+  float* fbeta_w;    /* f_beta.weight                [D,H]   */
+  float* fbeta_b;    /* f_beta.bias                  [D]     */
+  float* lin_w;      /* linear.weight                [V,H]   */
+  float* lin_b;      /* linear.bias                  [V]     */
+} dic_params;
+
+int dic_version(void);
+const char* dic_last_error(void);
+
+/* ---- weight pack -------------------------------------------------------------------
+ * Compute-layout copy of the parameters (storage dtype, fused/concatenated operands:
+ * [W_dec;W_beta], [W_ih|W_hh], b_ih+b_hh, ...).  Rebuild after every optimizer step. */
+size_t dic_pack_bytes(const dic_dims* dims, int dtype);
+int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* params, void* pack,
+                     void* stream);
+
+/* ---- teacher-forced training forward / backward ---------------------------------------
+ * Replaces CD_RNNDecoderWithSoftAttention.forward (depth_models.py:153-207),
+ * RNNDecoderWithSoftAttention.forward (base_caption_models.py:105-156),
+ * CD_/RNNDecoderWithHardAttention.forward (depth_models.py:580-634) and
+ * .eval_forward (depth_models.py:637-689).
+ *
+ *   f_rgb, f_depth : [B,L,D] annotations, feat_dtype (DIC_F32|DIC_BF16); f_depth may be NULL
+ *                    (base decoders).  RGB + depth are added once (depth_models.py:163).
+ *   captions       : [B,cap_stride] int64, column 0 = <start> (depth_models.py:160)
+ *   host_batch_sizes[T] : bs_valid per step, non-increasing (depth_models.py:182); the
+ *                    batch must be sorted by length, descending (util.py:95)
+ *   u              : [sum(bs), L] fp32 uniform draws for the hard variants, packed
+ *                    time-major like the reference's per-step torch.rand (attention.py:17,40)
+ *   dropout_mask   : [sum(bs), H] fp32, already scaled by 1/(1-p), or NULL (eval mode)
+ *   logits         : out [sum(bs), V] fp32 = PackedSequence.data (depth_models.py:204)
+ *   alphas         : out [B,T,L] fp32; the CALLER zero-fills it (depth_models.py:176).
+ *                    Required (it is also the state saved for backward).
+ *   workspace      : dic_train_workspace_bytes(); holds the saved state dic_decoder_backward reads.
+ */
+size_t dic_train_workspace_bytes(const dic_dims* dims, int dtype, int B, int T);
+
+int dic_decoder_forward(const dic_dims* dims, int dtype, int attn_mode, const void* pack,
+                        const void* f_rgb, const void* f_depth, int feat_dtype,
+                        const int64_t* captions, int cap_stride, const int32_t* host_batch_sizes,
+                        int T, int B, const float* u, float temp, const float* dropout_mask,
+                        float* logits, float* alphas, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* Backward of dic_decoder_forward (implicit autograd in the reference).
+ *   d_logits : [sum(bs), V] fp32 gradient of PackedSequence.data
+ *   d_alphas : [B,T,L] fp32 gradient of alphas, or NULL
+ *   grads    : 17 fp32 buffers in dic_params layout, OVERWRITTEN with the gradients
+ *   d_feats  : out [B,L,D] fp32 = dL/d(f_rgb + f_depth) (same tensor for both inputs), or NULL
+ *   f_rgb, f_depth, feat_dtype : the same annotation tensors the forward call received
+ *              (when no fused copy was needed the forward kept reading the caller's tensor)
+ */
+int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const void* pack,
+                         const void* f_rgb, const void* f_depth, int feat_dtype,
+                         const int64_t* captions, int cap_stride, const int32_t* host_batch_sizes,
+                         int T, int B, const float* d_logits, const float* d_alphas,
+                         const float* alphas, float temp, const float* dropout_mask,
+                         const dic_params* grads, float* d_feats, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- decoding -----------------------------------------------------------------------
+ * dic_decode_greedy replaces .sample / .batch_sample (depth_models.py:216-305, 698-789):
+ * fixed max_len steps, no early stop, next token = argmax (ties -> lowest id); no host
+ * sync per step (the reference copies to the host every step, depth_models.py:298-299).
+ *   tokens : out [B,max_len] int64;  alphas_out : out [max_len,B,L] fp32 or NULL;
+ *   logits_out : out [max_len,B,V] fp32 or NULL;  u : [max_len*B, L] for DIC_ATTN_GUMBEL_MAX.
+ *
+ * dic_decode_beam is NOT in the reference (greedy only); semantics are this build's own
+ * specification (oracle/decoder_oracle.py:beam_search).
+ *   tokens [B,max_len] int64 (best row, <end>-padded), lengths [B] int32, scores [B] fp32;
+ *   optional traces: back/toks [max_len,B,beam] int32, step_scores/lse [max_len,B,beam] fp32,
+ *   logits_out [max_len,B*beam,V] fp32.
+ */
+size_t dic_decode_workspace_bytes(const dic_dims* dims, int dtype, int B, int beam);
+
+int dic_decode_greedy(const dic_dims* dims, int dtype, int attn_mode, const void* pack,
+                      const void* f_rgb, const void* f_depth, int feat_dtype, int B,
+                      int start_id, int max_len, const float* u, int64_t* tokens,
+                      float* alphas_out, float* logits_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+int dic_decode_beam(const dic_dims* dims, int dtype, const void* pack, const void* f_rgb,
+                    const void* f_depth, int feat_dtype, int B, int beam, int start_id,
+                    int end_id, int max_len, int64_t* tokens, int32_t* lengths, float* scores,
+                    int32_t* back, int32_t* toks, float* step_scores, float* lse,
+                    float* logits_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- step-level operators ------------------------------------------------------------
+ * dic_attention_forward replaces Soft_Attention.forward / Hard_Attention.forward /
+ * Hard_Attention.Hard_sample as standalone modules (attention.py:81-95,132-167):
+ * feats [B,L,D] fp32, h [B,H] fp32 -> context [B,D] fp32, alpha [B,L] fp32.
+ * Weights are raw fp32 (enc_w [A,D], enc_b [A], dec_w [A,H], dec_b [A], full_w [A], full_b [1]).
+ */
+size_t dic_attention_workspace_bytes(const dic_dims* dims, int dtype, int B);
+int dic_attention_forward(const dic_dims* dims, int dtype, int attn_mode, const float* enc_w,
+                          const float* enc_b, const float* dec_w, const float* dec_b,
+                          const float* full_w, const float* full_b, const float* feats,
+                          const float* h, int B, const float* u, float temp, float* context,
+                          float* alpha, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One beam selection (the integer part of beam search, bit-exact vs the oracle's
+ * beam_select given identical inputs): scores [B,K] fp32, finished [B,K] uint8,
+ * logits [B*K,V] fp32, lse [B*K] fp32 -> new_scores [B,K], back [B,K] int32, tok [B,K] int32,
+ * new_finished [B,K] uint8.  cand = scores + (logits - lse), stable top-K, ties -> lowest index. */
+int dic_beam_select(const float* scores, const uint8_t* finished, const float* logits,
+                    const float* lse, int B, int K, int V, int end_id, float* new_scores,
+                    int32_t* back, int32_t* tok, uint8_t* new_finished, void* stream);
+
+/* Row-wise log-sum-exp of logits [R,V] fp32 -> lse [R] fp32. */
+int dic_row_lse(const float* logits, int R, int V, float* lse, void* stream);
+
+/* GEMM test hook: C[M,N] (fp32) = A[M,K] . B[N,K]^T (+bias[N]); a_dtype/b_dtype storage.
+ * engine 0 = CUDA-core FMA path, 1 = tcgen05/TMA path (bf16 operands, K % 64 == 0).
+ * workspace: dic_gemm_workspace_bytes (tensor maps / split-K partials). */
+int dic_gemm_nt(int engine, int M, int N, int K, const void* A, int a_dtype, const void* B,
+                int b_dtype, const float* bias, float* C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIC_H_ */
