@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the decoder hot path (BASELINE.json metric: train tokens/s, beam-5 captions/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this implementation
+    python bench.py --impl reference [--steps K] [--warmup W]      # reference CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): depth-soft training step -- forward + loss + backward
+(+ gradient all-reduce for N > 1) + AdamW -- bf16 storage, batch 256 per GPU, L=196, D=2048,
+A=E=H=128, V=10000, 20 decoder steps (all captions length 21), synthetic annotations.
+A "step" is one such pass over one batch; `value` = tokens (B*T*N) per second with the
+annotations resident in HBM; `e2e` = the same step through the module API with the
+annotations and captions in pinned HOST memory (H2D inside the timed region) and the loss
+read back (D2H).  One rank per GPU; weak scaling (256 per GPU).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L, D, A, E, H, V, T = 196, 2048, 128, 128, 128, 10000, 20
+LAM = 0.7   # doubly-stochastic regulariser weight (depth_train.py:216)
+
+
+# ----------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batch(B, seed, dtype=torch.float32):
+    """SURVEY.md 8d synthetic inputs: annotations U[0,1), captions with <start> ... <end>."""
+    g = torch.Generator().manual_seed(seed)
+    F_rgb = torch.rand(B, L, D, generator=g).to(dtype)
+    F_dep = torch.rand(B, L, D, generator=g).to(dtype)
+    caps = torch.randint(0, V - 4, (B, T + 1), generator=g)
+    caps[:, 0] = V - 4          # <start>
+    caps[:, T] = V - 3          # <end>
+    lengths = [T + 1] * B
+    return F_rgb, F_dep, caps, lengths
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# ----------------------------------------------------------------------------------------------
+def cpu_train_step_factory(B):
+    from oracle import decoder_oracle as O
+    w = {k: v.requires_grad_(True) for k, v in O.make_weights(A, E, D, H, V, seed=1234).items()}
+    F_rgb, F_dep, caps, lengths = synthetic_batch(B, 1235)
+    F_dep.requires_grad_(True)
+    opt = torch.optim.AdamW(list(w.values()), lr=1e-3)
+    targets = O.pack_targets(caps, lengths)
+
+    def step():
+        g = torch.Generator().manual_seed(0)
+        masks = [(torch.rand(B, H, generator=g) >= 0.5).float() * 2.0 for _ in range(T)]
+        # as written in the reference: att1 recomputed every step, [B,L,D] product materialised
+        logits, _, alphas = O.decoder_forward(w, F_rgb, F_dep, caps, lengths, dropout_masks=masks, hoist=False)
+        loss = O.caption_loss(logits, targets, V - 1, alphas, LAM)
+        opt.zero_grad(set_to_none=True)
+        F_dep.grad = None
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    return step
+
+
+def time_cpu(B, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_train_step_factory(B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return B * T * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch
+    tps, spstep = time_cpu(B, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    sample = f"fwd+loss+bwd+AdamW on {B} of the 256 captions per step (fp32, oracle port of the reference CPU path, as written)"
+    line = {
+        "impl": "reference", "metric": "train_tokens_per_s", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, args.batch),
+        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, batch):
+    return {"workload": "depth-soft teacher-forced training step (fwd+loss+bwd+AdamW), BASELINE.json configs[1]",
+            "batch_per_gpu": batch, "global_batch": batch * n_gpus, "decoder_steps": T, "L": L, "D": D, "A": A,
+            "E": E, "H": H, "V": V, "storage": "bf16 annotations/att1/GEMM operands, fp32 accumulate and state",
+            "l2_policy": "inputs larger than L2 (annotations 2 x 205 MB bf16 per GPU, workspace ~0.5 GB)",
+            "parallelism": f"dp{n_gpus}"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import depth_image_captioning_pub_b200 as P
+    from depth_image_captioning_pub_b200 import _lib
+    from oracle import decoder_oracle as O    # weights only (make_weights); never on the timed path
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B = args.batch
+    m = P.CD_RNNDecoderWithSoftAttention(A, E, D, H, V)
+    m.load_state_dict(O.make_weights(A, E, D, H, V, seed=1234))
+    m.precision = args.precision
+    m = m.to(dev).train()
+    params = [p for p in m.parameters()]
+    opt = torch.optim.AdamW(params, lr=1e-3, fused=True)
+    feat_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
+    F_rgb_h, F_dep_h, caps_h, lengths = synthetic_batch(B, 1235 + rank, feat_dtype)
+    F_rgb_h, F_dep_h, caps_h = F_rgb_h.pin_memory(), F_dep_h.pin_memory(), caps_h.pin_memory()
+    from depth_image_captioning_pub_b200.engine import batch_sizes_from_lengths
+    targets = O.pack_targets(caps_h, lengths).to(dev)
+    F_rgb = F_rgb_h.to(dev)
+    F_dep = F_dep_h.to(dev).requires_grad_(True)     # the depth CNN is trained: dL/dF_depth is part of the step
+    caps = caps_h.to(dev)
+    flat = None
+    if world > 1:
+        n = sum(p.numel() for p in params)
+        flat = torch.empty(n, dtype=torch.float32, device=dev)
+
+    def train_step(fr, fd, cp):
+        out, alphas = m(fr, fd, cp, lengths)
+        loss = torch.nn.functional.cross_entropy(out.data, targets, ignore_index=V - 1)
+        loss = loss + LAM * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+        loss.backward()
+        if world > 1:   # data parallel: one flat fp32 NCCL all-reduce over NVLink
+            o = 0
+            for p in params:
+                flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
+                o += p.numel()
+            dist.all_reduce(flat)
+            flat.mul_(1.0 / world)
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p))
+                o += p.numel()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        fd.grad = None
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident timing (value) -------------------------------------------------------
+    for _ in range(args.warmup):
+        train_step(F_rgb, F_dep, caps)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.dic_launch_count()
+    ms = timed(lambda: train_step(F_rgb, F_dep, caps), args.steps)
+    launches = (lib.dic_launch_count() - l0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    tokens_per_step = B * T * world
+    value = tokens_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> module API -> loss on the host ------------------------
+    def e2e_step():
+        fr = F_rgb_h.to(dev, non_blocking=True)
+        fd = F_dep_h.to(dev, non_blocking=True).requires_grad_(True)
+        cp = caps_h.to(dev, non_blocking=True)
+        return float(train_step(fr, fd, cp).item())
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = F_rgb_h.numel() * F_rgb_h.element_size() * 2 + caps_h.numel() * 8
+
+    # ---- per-kernel-class CUDA-event profile of the same steps (roofline) -------------------------
+    lib.dic_profile_enable(1)
+    timed(lambda: train_step(F_rgb, F_dep, caps), args.steps)
+    prof = _lib.profile_read()
+    lib.dic_profile_enable(0)
+    peak, peak_src = measured_peaks()
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] // args.steps}
+               for k, v in prof.items() if v[1]}
+    dom = max(("attn_step_fwd", "attn_step_bwd"), key=lambda k: prof[k][0])
+    dms, dcnt, dbytes = prof[dom]
+    achieved = (dbytes / dcnt) / (dms / dcnt * 1e-3) / 1e9 if dcnt else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dbytes / dcnt if dcnt else None,
+                "avg_launch_us": dms / dcnt * 1e3 if dcnt else None, "launches_per_step": dcnt // args.steps}
+
+    # ---- beam-5 decode (second half of the BASELINE metric), 128 images per GPU --------------------
+    extra = {}
+    if not args.no_beam:
+        m.eval()
+        Bd = args.decode_batch
+        voc = O.synthetic_vocab(V)
+        fr, fd = F_rgb[:Bd].contiguous(), F_dep[:Bd].detach().contiguous()
+        for _ in range(2):
+            m.beam_search(fr, fd, voc, beam=5, max_length=T)
+        ms_b = timed(lambda: m.beam_search(fr, fd, voc, beam=5, max_length=T), args.steps)
+        extra["beam5_captions_per_s"] = Bd * world * args.steps / (ms_b * 1e-3)
+        extra["beam5_config"] = {"images_per_gpu": Bd, "beam": 5, "max_len": T}
+        ms_g = timed(lambda: m.batch_sample(fr, fd, voc, max_length=T), args.steps)
+        extra["greedy_captions_per_s"] = Bd * world * args.steps / (ms_g * 1e-3)
+        m.train()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        tps, _ = time_cpu(args.cpu_batch, args.cpu_steps, 1)
+        cpu = {"value": tps, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{args.cpu_steps} fwd+loss+bwd+AdamW steps on {args.cpu_batch} of the 256 captions "
+                         f"(fp32, oracle port of the reference CPU path as written)"}
+
+    if rank == 0:
+        line = {
+            "metric": "train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic", "config": workload_config(world, B),
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kernels, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=256, help="captions per GPU")
+    ap.add_argument("--decode-batch", type=int, default=128)
+    ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-beam", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,11 @@ PROTOTYPES = {
     "dic_beam_select": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dic_row_lse": (_I, [_P, _I, _I, _P, _P]),
     "dic_gemm_nt": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
+    "dic_launch_count": (C.c_longlong, []),
+    "dic_profile_classes": (_I, []),
+    "dic_profile_class_name": (C.c_char_p, [_I]),
+    "dic_profile_enable": (None, [_I]),
+    "dic_profile_read": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -106,6 +111,17 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         raise DicError(f"libdic.so version {lib.dic_version()} != 100; rebuild")
     _lib = lib
     return lib
+
+
+def profile_read():
+    """-> {class: (ms, launches, algorithmic_bytes)} since the last dic_profile_enable(1)/read."""
+    lib = load()
+    n = lib.dic_profile_classes()
+    ms = (C.c_float * n)()
+    cnt = (C.c_longlong * n)()
+    by = (C.c_double * n)()
+    check(lib.dic_profile_read(ms, cnt, by))
+    return {lib.dic_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i]), float(by[i])) for i in range(n)}
 
 
 def check(rc: int) -> None:

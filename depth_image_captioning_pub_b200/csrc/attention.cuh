@@ -240,6 +240,8 @@ inline int launch_attn_step(const AttnFwdArgs& p, int images, int KB, cudaStream
   if (images <= 0) return 0;
   dim3 grid(cdiv(p.D, kAttnDChunk), images);
   const size_t smem = attn_fwd_smem_bytes(p.L, p.A, KB);
+  // algorithmic bytes: annotations + att1 once per image-step
+  ProfScope prof(P_ATTN_FWD, st, (double)images * p.L * ((double)p.D + p.A) * sizeof(ST));
 #define DIC_ATTN_CASE(K)                                                                          \
   case K: {                                                                                       \
     static bool attr_set = false;                                                                 \
@@ -409,6 +411,7 @@ inline int launch_attn_bwd(const AttnBwdArgs& p, int rows, cudaStream_t st) {
                                   200 * 1024));
     attr_set = true;
   }
+  ProfScope prof(P_ATTN_BWD, st, (double)rows * p.L * ((double)p.D + p.A) * sizeof(ST));
   attn_bwd_kernel<ST><<<rows, kAttnBwdThreads, smem, st>>>(p);
   DIC_LAUNCH_CHECK();
   return 0;
@@ -471,6 +474,7 @@ __global__ void __launch_bounds__(256) datt1_kernel(const Datt1Args p) {
 template <typename ST>
 inline int launch_datt1(const Datt1Args& p, cudaStream_t st) {
   dim3 grid(cdiv(p.L, 32), p.B);
+  ProfScope prof(P_DATT1, st, (double)p.B * p.L * p.A * sizeof(ST) * 2);
   datt1_kernel<ST><<<grid, 256, 0, st>>>(p);
   DIC_LAUNCH_CHECK();
   return 0;

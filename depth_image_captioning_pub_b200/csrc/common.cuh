@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <vector>
+
 #include "../../include/dic.h"
 
 namespace dic {
@@ -30,6 +33,7 @@ extern thread_local char g_err[512];
 
 #define DIC_LAUNCH_CHECK()                                                                   \
   do {                                                                                       \
+    dic::g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
     cudaError_t _e = cudaGetLastError();                                                     \
     if (_e != cudaSuccess)                                                                   \
       DIC_FAIL(-3, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
@@ -40,6 +44,48 @@ extern thread_local char g_err[512];
     int _r = (expr);        \
     if (_r != 0) return _r; \
   } while (0)
+
+// ---- launch counter and optional per-kernel-class CUDA-event profiling ------------------------
+// (bench.py reads these through dic_launch_count / dic_profile_*; off by default, no cost)
+inline std::atomic<long long> g_launches{0};
+
+enum ProfClass { P_ATTN_FWD = 0, P_ATTN_BWD, P_DATT1, P_GEMM_TC, P_GEMM_FMA, P_LSTM, P_FUSE, P_COLSUM, P_N };
+inline const char* prof_class_name(int c) {
+  static const char* names[P_N] = {"attn_step_fwd", "attn_step_bwd", "datt1", "gemm_tcgen05",
+                                   "gemm_fma", "lstm_pointwise", "fuse_feats", "colsum"};
+  return (c >= 0 && c < P_N) ? names[c] : "?";
+}
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[P_N];   // start/end pairs
+  size_t used[P_N] = {0};
+  double bytes[P_N] = {0};            // algorithmic bytes attributed by the launch site
+};
+inline ProfState g_prof;
+
+struct ProfScope {
+  int cls;
+  cudaStream_t st;
+  bool active;
+  ProfScope(int c, cudaStream_t s, double algo_bytes = 0.0) : cls(c), st(s), active(g_prof.on) {
+    if (!active) return;
+    auto& v = g_prof.ev[cls];
+    size_t& u = g_prof.used[cls];
+    while (v.size() < u + 2) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      v.push_back(e);
+    }
+    cudaEventRecord(v[u], st);
+    g_prof.bytes[cls] += algo_bytes;
+  }
+  ~ProfScope() {
+    if (!active) return;
+    size_t& u = g_prof.used[cls];
+    cudaEventRecord(g_prof.ev[cls][u + 1], st);
+    u += 2;
+  }
+};
 
 // ---- dtype-erased scalar access --------------------------------------------------------
 __device__ __forceinline__ float ld_as_float(const void* p, size_t i, int is_bf16) {

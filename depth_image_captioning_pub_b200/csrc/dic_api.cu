@@ -523,6 +523,33 @@ using namespace dic;
 extern "C" {
 
 int dic_version(void) { return DIC_VERSION; }
+
+long long dic_launch_count(void) { return g_launches.load(); }
+int dic_profile_classes(void) { return P_N; }
+const char* dic_profile_class_name(int c) { return prof_class_name(c); }
+void dic_profile_enable(int on) {
+  g_prof.on = on != 0;
+  for (int c = 0; c < P_N; ++c) { g_prof.used[c] = 0; g_prof.bytes[c] = 0; }
+}
+// Sums the CUDA-event durations recorded since dic_profile_enable(1) (synchronises on the
+// recorded events) and resets the counters.  ms/launches/bytes: arrays of dic_profile_classes().
+int dic_profile_read(float* ms, long long* launches, double* bytes) {
+  for (int c = 0; c < P_N; ++c) {
+    float tot = 0.f;
+    for (size_t i = 0; i + 1 < g_prof.used[c]; i += 2) {
+      float t = 0.f;
+      DIC_CUDA(cudaEventSynchronize(g_prof.ev[c][i + 1]));
+      DIC_CUDA(cudaEventElapsedTime(&t, g_prof.ev[c][i], g_prof.ev[c][i + 1]));
+      tot += t;
+    }
+    ms[c] = tot;
+    launches[c] = (long long)(g_prof.used[c] / 2);
+    bytes[c] = g_prof.bytes[c];
+    g_prof.used[c] = 0;
+    g_prof.bytes[c] = 0;
+  }
+  return 0;
+}
 const char* dic_last_error(void) { return g_err; }
 
 size_t dic_pack_bytes(const dic_dims* dims, int dtype) {

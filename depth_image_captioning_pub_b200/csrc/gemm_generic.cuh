@@ -154,6 +154,7 @@ inline int gemm_generic(const GemmArgs& g, cudaStream_t st) {
   if (g.splits > 1 && g.split_mode == 0 && (g.c_bf16 || g.sig_hi > g.sig_lo))
     DIC_FAIL(-4, "gemm_generic: atomic split-K needs fp32 C and no activation");
   if (g.accumulate && g.c_bf16) DIC_FAIL(-4, "gemm_generic: accumulate needs fp32 C");
+  ProfScope prof(P_GEMM_FMA, st);
   const long long tiles128 = (long long)cdiv(g.M, 128) * cdiv(g.N, 128) * g.batch * g.splits;
   if (tiles128 >= 148 && g.M >= 128 && g.N >= 128) {
     dim3 grid(cdiv(g.N, 128), cdiv(g.M, 128), g.batch * g.splits);

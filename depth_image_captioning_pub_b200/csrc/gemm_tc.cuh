@@ -346,6 +346,7 @@ inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(cdiv(g.N, BN), cdiv(g.M, kTcBM), p.splits);
+  ProfScope prof(P_GEMM_TC, st);
   tc_gemm_kernel<BN><<<grid, kTcThreads, tc_smem_bytes<BN>(), st>>>(tmA, tmB, p);
   DIC_LAUNCH_CHECK();
   return 0;

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
 template <typename ST>
 inline int launch_lstm_fwd(const LstmFwdArgs& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
+  ProfScope prof(P_LSTM, st);
   lstm_fwd_kernel<ST><<<cdiv(p.rows * p.H, 256), 256, 0, st>>>(p);
   DIC_LAUNCH_CHECK();
   return 0;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
 template <typename ST>
 inline int launch_lstm_bwd(const LstmBwdArgs& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
+  ProfScope prof(P_LSTM, st);
   lstm_bwd_kernel<ST><<<cdiv(p.rows * p.H, 256), 256, 0, st>>>(p);
   DIC_LAUNCH_CHECK();
   return 0;

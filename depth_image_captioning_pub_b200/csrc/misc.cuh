@@ -63,6 +63,7 @@ template <typename ST>
 inline int launch_fuse_feats(const void* rgb, const void* dep, int feat_bf16, ST* fsum, float* meanF,
                              int B, int L, int D, cudaStream_t st) {
   dim3 grid(cdiv(D, 1024), B);
+  ProfScope prof(P_FUSE, st);
   if (feat_bf16)
     fuse_feats_kernel<bf16, ST><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(rgb),
                                                      reinterpret_cast<const bf16*>(dep), fsum, meanF, L, D);
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ sr
 
 inline int launch_colsum(const void* src, int src_bf16, int R, int C, long long ld, float* dst,
                          cudaStream_t st) {
+  ProfScope prof(P_COLSUM, st);
   DIC_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * C, st));
   if (R <= 0 || C <= 0) return 0;
   int chunks = cdiv(R, 256);

@@ -185,6 +185,15 @@ int dic_beam_select(const float* scores, const uint8_t* finished, const float* l
 /* Row-wise log-sum-exp of logits [R,V] fp32 -> lse [R] fp32. */
 int dic_row_lse(const float* logits, int R, int V, float* lse, void* stream);
 
+/* ---- instrumentation (bench.py) ---------------------------------------------------------
+ * dic_launch_count: kernels launched by this library since load.  dic_profile_*: optional
+ * CUDA-event timing per kernel class on the launching stream (off by default). */
+long long dic_launch_count(void);
+int dic_profile_classes(void);
+const char* dic_profile_class_name(int cls);
+void dic_profile_enable(int on);
+int dic_profile_read(float* ms, long long* launches, double* bytes);
+
 /* GEMM test hook: C[M,N] (fp32) = A[M,K] . B[N,K]^T (+bias[N]); a_dtype/b_dtype storage.
  * engine 0 = CUDA-core FMA path, 1 = tcgen05/TMA path (bf16 operands, K % 64 == 0).
  * workspace: dic_gemm_workspace_bytes (tensor maps / split-K partials). */
