@@ -78,6 +78,8 @@ PROTOTYPES = {
     "dic_beam_select": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dic_row_lse": (_I, [_P, _I, _I, _P, _P]),
     "dic_gemm_nt": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
+    "dic_gemm_ex": (_I, [_I, _I, _I, _I, _P, _I, C.c_longlong, C.c_longlong, _P, _I, C.c_longlong, C.c_longlong,
+                         _P, _P, C.c_longlong, _I, _P]),
     "dic_launch_count": (C.c_longlong, []),
     "dic_profile_classes": (_I, []),
     "dic_profile_class_name": (C.c_char_p, [_I]),

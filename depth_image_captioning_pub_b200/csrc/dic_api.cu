@@ -47,6 +47,27 @@ static int gemm(const GemmArgs& g, cudaStream_t st) {
   return gemm_generic(g, st);
 }
 
+// Dense fp32 output with a long contraction and few output tiles (weight gradients, dHout):
+// split K so the grid covers the SMs about twice; C is zero-filled and accumulated atomically.
+static int gemm_splitk(GemmArgs g, cudaStream_t st) {
+  int s = 1;
+  if (g.ldc == g.N && !g.c_bf16 && !g.accumulate && g.batch == 1) {
+    if (tc_gemm_eligible(g)) {
+      const long long tiles = (long long)cdiv(g.M, kTcBM) * cdiv(g.N, 128);
+      const int kb = cdiv(g.K, kTcBK);
+      s = (int)((2 * 148 + tiles - 1) / tiles);
+      if (s > kb / 4) s = kb / 4;     // keep >= 4 k-blocks per CTA so the TMA/MMA pipeline fills
+    } else {
+      s = pick_splits(g.M, g.N, g.K);
+    }
+    if (s < 1) s = 1;
+  }
+  g.splits = s;
+  g.split_mode = 0;
+  if (s > 1) DIC_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.ldc, st));
+  return gemm(g, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // shared prologue: Fsum, meanF, att1 (K0)
 // ---------------------------------------------------------------------------------------------
@@ -102,13 +123,14 @@ static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long 
   const int is_bf16 = sizeof(ST) == 2;
   GemmArgs g = gemm_args_nt(X, is_bf16, XW, pk.Wg(), is_bf16, XW, gate_part, 0, 4 * d.H, rows, 4 * d.H,
                             (int)XW, nullptr);
-  int s = pick_splits(rows, 4 * d.H, (int)XW);
+  // only a handful of 128x128 output tiles exist (M = batch, N = 4H): split K across the SMs
+  int s = tc_gemm_eligible(g) ? cdiv((int)XW, kTcBK) : pick_splits(rows, 4 * d.H, (int)XW);
   if (s > kGateSplitsMax) s = kGateSplitsMax;
   g.splits = s;
   g.split_mode = 1;
   g.split_stride = (long long)rows_alloc * 4 * d.H;
   *splits_out = s;
-  return gemm_generic(g, st);
+  return gemm(g, st);
 }
 
 // =============================================================================================
@@ -250,11 +272,21 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   DIC_CUDA(cudaMemsetAsync(dwfull_part, 0, sizeof(float) * TB * A, st));
   DIC_CUDA(cudaMemsetAsync(dbfull_part, 0, sizeof(float) * TB, st));
 
+  // bf16 mode: the two contractions over d_logits take a bf16 copy (tensor-core operand)
+  const void* dl = d_logits;
+  int dl_bf16 = 0;
+  if (is_bf16) {
+    void* dl16 = ws + lay.dlogits16;
+    DIC_TRY(launch_copy2d(d_logits, V, dl16, V, 1, total, V, st));
+    dl = dl16;
+    dl_bf16 = 1;
+  }
+
   // dHout = d_logits . W_out   (all packed rows)
   {
-    GemmArgs g = gemm_args_nt(d_logits, 0, V, pk.Wout(), is_bf16, 0, dHout, 0, H, total, H, V, nullptr);
+    GemmArgs g = gemm_args_nt(dl, dl_bf16, V, pk.Wout(), is_bf16, 0, dHout, 0, H, total, H, V, nullptr);
     g.b_n = 1; g.b_k = H;
-    DIC_TRY(gemm(g, st));
+    DIC_TRY(gemm_splitk(g, st));
   }
 
   const float inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
@@ -331,12 +363,9 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 
   auto wgrad = [&](const ST* Aop, long long a_ld, int M, const ST* Bop, long long b_ld, int N, int K,
                    float* C, long long ldc) -> int {
-    DIC_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
     GemmArgs g = gemm_args_nt(Aop, is_bf16, 0, Bop, is_bf16, 0, C, 0, ldc, M, N, K, nullptr);
     g.a_m = 1; g.a_k = a_ld; g.b_n = 1; g.b_k = b_ld;
-    g.splits = pick_splits(M, N, K);
-    g.split_mode = 0;
-    return gemm(g, st);
+    return gemm_splitk(g, st);
   };
   // [dW_ih | dW_hh] = dgates^T . [emb|zg|h]
   DIC_TRY(wgrad(G, GW, 4 * H, XH, XW, E + D, (int)TB, gr.w_ih, E + D));
@@ -372,11 +401,9 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 
   // linear (vocabulary projection)
   {
-    DIC_CUDA(cudaMemsetAsync(gr.lin_w, 0, sizeof(float) * (size_t)V * H, st));
-    GemmArgs g = gemm_args_nt(d_logits, 0, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
+    GemmArgs g = gemm_args_nt(dl, dl_bf16, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
     g.a_m = 1; g.a_k = V; g.b_n = 1; g.b_k = H;
-    g.splits = pick_splits(V, H, total);
-    DIC_TRY(gemm(g, st));
+    DIC_TRY(gemm_splitk(g, st));
     DIC_TRY(launch_colsum(d_logits, 0, total, V, V, gr.lin_b, st));
   }
 
@@ -823,6 +850,23 @@ int dic_gemm_nt(int engine, int M, int N, int K, const void* A, int a_dtype, con
                 const float* bias, float* C, void* stream) {
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) DIC_FAIL(-1, "bad argument");
   GemmArgs g = gemm_args_nt(A, a_dtype == DIC_BF16, K, B, b_dtype == DIC_BF16, K, C, 0, N, M, N, K, bias);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (engine == 1) {
+    if (!tc_gemm_eligible(g)) DIC_FAIL(-5, "shape/dtype not eligible for the tcgen05 engine");
+    return tc_gemm(g, st);
+  }
+  return gemm_generic(g, st);
+}
+
+int dic_gemm_ex(int engine, int M, int N, int K, const void* A, int a_dtype, long long a_m, long long a_k,
+                const void* B, int b_dtype, long long b_n, long long b_k, const float* bias, float* C,
+                long long ldc, int splits, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || splits < 1) DIC_FAIL(-1, "bad argument");
+  GemmArgs g = gemm_args_nt(A, a_dtype == DIC_BF16, a_m, B, b_dtype == DIC_BF16, b_n, C, 0, ldc, M, N, K, bias);
+  g.a_k = a_k;
+  g.b_k = b_k;
+  g.splits = splits;
+  g.split_mode = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (engine == 1) {
     if (!tc_gemm_eligible(g)) DIC_FAIL(-5, "shape/dtype not eligible for the tcgen05 engine");

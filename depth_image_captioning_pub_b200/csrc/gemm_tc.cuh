@@ -70,9 +70,24 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major, 128B-swizzled operand tile as TMA lays it down from a row-major [K, MN] matrix:
+// box = 64 MN-elements (128 bytes) x BK rows; atom = 64 MN x 8 K = 1024 bytes; the next 8 K rows
+// are 1024 bytes further (SBO), the next block of 64 MN elements is a separate box BK*128 bytes
+// further (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((kTcBK * 128) >> 4) << 16;            // leading byte offset: next 64-wide MN block
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: next 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, M x N; a_mn / b_mn select MN-major operands.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -118,7 +133,7 @@ constexpr size_t tc_smem_bytes() {
   return 1024 /*align slack*/ + (size_t)kTcStages * (kTcBM * kTcBK * 2 + BN * kTcBK * 2) + 256;
 }
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -172,26 +187,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
         mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-        tma_load_2d(sa, &tmA, full_bar(stage), kb * kTcBK, m0);
-        tma_load_2d(sb, &tmB, full_bar(stage), kb * kTcBK, n0);
+        if (A_MN) {
+#pragma unroll
+          for (int h = 0; h < kTcBM / 64; ++h)
+            tma_load_2d(sa + h * (kTcBK * 128), &tmA, full_bar(stage), m0 + 64 * h, kb * kTcBK);
+        } else {
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * kTcBK, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int h = 0; h < BN / 64; ++h)
+            tma_load_2d(sb + h * (kTcBK * 128), &tmB, full_bar(stage), n0 + 64 * h, kb * kTcBK);
+        } else {
+          tma_load_2d(sb, &tmB, full_bar(stage), kb * kTcBK, n0);
+        }
         if (++stage == kTcStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, BN, A_MN, B_MN);
+      // K advance of one UMMA (16 elements): 32 bytes inside the atom row for K-major operands,
+      // 16 rows of 128 bytes for MN-major operands (address field is in 16-byte units)
+      constexpr uint32_t a_kstep = A_MN ? (16 * 128) >> 4 : 32 >> 4;
+      constexpr uint32_t b_kstep = B_MN ? (16 * 128) >> 4 : 32 >> 4;
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        const uint64_t adesc = umma_desc_kmajor_sw128(sa), bdesc = umma_desc_kmajor_sw128(sb);
+        const uint64_t adesc = A_MN ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
+        const uint64_t bdesc = B_MN ? umma_desc_mnmajor_sw128(sb) : umma_desc_kmajor_sw128(sb);
 #pragma unroll
         for (int k = 0; k < kTcBK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the address field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
         if (++stage == kTcStages) { stage = 0; phase ^= 1; }
@@ -287,14 +318,14 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
 }
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with row stride ld (elements);
-// box = [box_rows, 64 cols], 128B swizzle, zero fill out of bounds.
+// box = [box_rows, 64 cols] (64 bf16 = 128 bytes), 128B swizzle, zero fill out of bounds.
 inline int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
                           int box_rows) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) DIC_FAIL(-6, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -312,24 +343,49 @@ inline bool tc_enabled() {
   return v == 1;
 }
 
+// operand layouts the engine takes: K-major (k stride 1) or MN-major (m/n stride 1); the other
+// stride must keep TMA's 16-byte global stride rule
+inline bool tc_operand_ok(const void* p, long long s_mn, long long s_k) {
+  if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+  if (s_k == 1) return s_mn % 8 == 0 && s_mn > 0;
+  if (s_mn == 1) return s_k % 8 == 0 && s_k > 0;
+  return false;
+}
+
 inline bool tc_gemm_eligible(const GemmArgs& g) {
   if (!tc_enabled()) return false;
   if (!g.a_bf16 || !g.b_bf16) return false;
-  if (g.a_k != 1 || g.b_k != 1) return false;
+  if (!tc_operand_ok(g.A, g.a_m, g.a_k) || !tc_operand_ok(g.B, g.b_n, g.b_k)) return false;
   if (g.batch != 1 || g.accumulate) return false;
-  if ((g.a_m % 8) || (g.b_n % 8)) return false;   // 16-byte global strides for TMA
-  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
   if (g.K < 16 || g.M < 1 || g.N < 8) return false;
   if ((long long)g.M * g.N < 128LL * 128LL) return false;   // tiny outputs: the FMA engine is as fast
   if (g.splits > 1 && g.split_mode == 0 && (g.c_bf16 || g.sig_hi > g.sig_lo)) return false;
   return true;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& p, dim3 grid,
+                          cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc_smem_bytes<BN>()));
+    attr_set = true;
+  }
+  tc_gemm_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, tc_smem_bytes<BN>(), st>>>(tmA, tmB, p);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
 inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
   constexpr int BN = 128;
+  const bool a_mn = g.a_k != 1, b_mn = g.b_k != 1;
   CUtensorMap tmA, tmB;
-  DIC_TRY(make_tmap_bf16(&tmA, g.A, g.M, g.K, g.a_m, kTcBM));
-  DIC_TRY(make_tmap_bf16(&tmB, g.B, g.N, g.K, g.b_n, BN));
+  // K-major: matrix [MN rows, K cols], box MN x 64(K).  MN-major: matrix [K rows, MN cols], box 64(K) x 64(MN).
+  if (a_mn) DIC_TRY(make_tmap_bf16(&tmA, g.A, g.K, g.M, g.a_k, kTcBK));
+  else      DIC_TRY(make_tmap_bf16(&tmA, g.A, g.M, g.K, g.a_m, kTcBM));
+  if (b_mn) DIC_TRY(make_tmap_bf16(&tmB, g.B, g.K, g.N, g.b_k, kTcBK));
+  else      DIC_TRY(make_tmap_bf16(&tmB, g.B, g.N, g.K, g.b_n, BN));
   TcArgs p;
   p.C = g.C; p.bias = g.bias; p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.c_bf16 = g.c_bf16;
   const int num_kb = cdiv(g.K, kTcBK);
@@ -339,17 +395,12 @@ inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
     DIC_FAIL(-4, "tc_gemm: partial-buffer split-K needs splits <= K/64");
   p.split_mode = g.split_mode; p.split_stride = g.split_stride;
   p.alpha = g.alpha; p.sig_lo = g.sig_lo; p.sig_hi = g.sig_hi;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DIC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)tc_smem_bytes<BN>()));
-    attr_set = true;
-  }
   dim3 grid(cdiv(g.N, BN), cdiv(g.M, kTcBM), p.splits);
   ProfScope prof(P_GEMM_TC, st);
-  tc_gemm_kernel<BN><<<grid, kTcThreads, tc_smem_bytes<BN>(), st>>>(tmA, tmB, p);
-  DIC_LAUNCH_CHECK();
-  return 0;
+  if (!a_mn && !b_mn) return tc_gemm_launch<BN, false, false>(tmA, tmB, p, grid, st);
+  if (!a_mn && b_mn) return tc_gemm_launch<BN, false, true>(tmA, tmB, p, grid, st);
+  if (a_mn && !b_mn) return tc_gemm_launch<BN, true, false>(tmA, tmB, p, grid, st);
+  return tc_gemm_launch<BN, true, true>(tmA, tmB, p, grid, st);
 }
 
 }  // namespace dic

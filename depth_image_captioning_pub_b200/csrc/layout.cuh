@@ -74,7 +74,7 @@ constexpr int kGateSplitsMax = 16;
 // Training workspace (forward state saved for backward + backward scratch).
 struct TrainLayout {
   size_t Fsum, meanF, att1, XH, HP, Z, acts, c_all, gate_part, Hdrop;
-  size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec;
+  size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16;
   size_t bytes;
   size_t XW, GW;
   int es;
@@ -107,6 +107,7 @@ struct TrainLayout {
     dXemb = c.take(sizeof(float) * TB * d.E);
     dmeanF = c.take(sizeof(float) * B * d.D);
     tmpvec = c.take(sizeof(float) * (GW + 16));
+    dlogits16 = c.take(dtype == DIC_BF16 ? TB * d.V * 2 : 16);   // bf16 copy of d_logits (GEMM operand)
     bytes = c.off;
   }
 };

@@ -200,6 +200,13 @@ int dic_profile_read(float* ms, long long* launches, double* bytes);
 int dic_gemm_nt(int engine, int M, int N, int K, const void* A, int a_dtype, const void* B,
                 int b_dtype, const float* bias, float* C, void* stream);
 
+/* General form: A(m,k) = A[m*a_m + k*a_k], B(n,k) = B[n*b_n + k*b_k] (element strides), so
+ * K-major and MN-major operands of both engines can be exercised; splits > 1 = atomic split-K
+ * into a zero-filled C. */
+int dic_gemm_ex(int engine, int M, int N, int K, const void* A, int a_dtype, long long a_m,
+                long long a_k, const void* B, int b_dtype, long long b_n, long long b_k,
+                const float* bias, float* C, long long ldc, int splits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
