@@ -1,24 +1,33 @@
-// Fused additive-attention step kernels (the HBM-bound heart of the decoder timestep).
+// Additive-attention step kernels (the HBM-bound heart of the decoder timestep).
 //
-// Forward, one launch per timestep, replaces the ATen sequence
+// Forward, per timestep, replaces the ATen sequence
 //   add, relu_, matmul(+bias), softmax, mul -> [B,L,D] temporary, sum, f_beta sigmoid, mul, cat
-// of attention.py:84-93 + depth_models.py:189-192 with a single pass over the annotations:
-//   e[l]  = relu(att1[l,:] + att2) . w_full + b_full
-//   alpha = softmax_L(e)        | softmax((e+g)/temp)   | one_hot(argmax(e+g))
-//   z     = sum_l alpha[l] F[l,:]          (streamed, 16-byte coalesced loads, fp32 registers)
-//   zg    = beta * z            -> written straight into the LSTM input row ([emb | zg | h])
+// of attention.py:84-93 + depth_models.py:189-192 with two launches:
+//   (a) attn_alpha_kernel   e[l] = relu(att1[l,:] + att2) . w_full + b_full
+//                           alpha = softmax_L(e) | softmax((e+g)/temp) | one_hot(argmax(e+g))
+//       one CTA per image (reads the 50 KB att1 slab once for all beams of the image);
+//   (b) attn_context_kernel z = sum_l alpha[l] F[l,:],  zg = beta * z
+//       a pure streaming pass over the annotations: grid = (D/256 column chunks, images),
+//       128 threads, 16-byte coalesced loads with 7 rows in flight per thread, fp32 register
+//       accumulators, deterministic cross-warp reduction in shared memory; zg is written
+//       straight into the LSTM input row ([emb | zg | h]).
 // att1 = F.W_enc^T + b_enc is loop invariant and hoisted out of the time loop (K0).
+// A context CTA serves the KB rows (beams) that share one image, so the annotations are read
+// once per image-step, not once per beam.
 //
-// Grid = (D chunks of 512 columns, images).  A CTA serves the KB rows (beams) that share one
-// image, so the annotations are read once per image-step, not once per beam.
+// (An earlier single-kernel version ran energies, softmax and the context pass in one CTA; ncu
+// showed 34% of HBM peak: every CTA idled the memory system during its energy/softmax phases and
+// the 1024-CTA grid was 1.15 waves.  See profiles/.)
 #pragma once
 #include "common.cuh"
 
 namespace dic {
 
-constexpr int kAttnThreads = 256;
-constexpr int kAttnDChunk = 512;   // columns per CTA (64 threads x 8 columns)
-constexpr int kAttnRowGroups = kAttnThreads / (kAttnDChunk / 8);  // 4
+constexpr int kAlphaThreads = 256;
+constexpr int kCtxThreads = 128;
+constexpr int kCtxCols = 256;                       // columns per context CTA (32 lanes x 8)
+constexpr int kCtxGroups = kCtxThreads / 32;        // 4 row groups (one warp each)
+constexpr int kCtxUnroll = 7;                       // rows in flight per thread
 
 struct AttnFwdArgs {
   const void* F;        // [images, L, D] ST
@@ -27,7 +36,7 @@ struct AttnFwdArgs {
   const float* w_full;  // [A]
   const float* b_full;  // [1]
   const float* u;       // [rows, L] uniform draws or null
-  float* alpha_out;     // row r at alpha_out + r*alpha_stride, or null
+  float* alpha_out;     // row r at alpha_out + r*alpha_stride (required: (a) -> (b) hand-off)
   long long alpha_stride;
   float* z_out;         // [rows, D] fp32 or null (saved for backward)
   void* zg_out;         // ST, row r at zg_out + r*zg_stride
@@ -37,70 +46,71 @@ struct AttnFwdArgs {
   float inv_temp;
 };
 
-inline size_t attn_fwd_smem_bytes(int L, int A, int KB) {
-  // w[A] | att2[KB][A] | e[KB][L] | part[3][KB][DCH] | idx[KB]
+// ---------------------------------------------------------------------------------------------
+// (a) energies + normalisation.  Half-warp per annotation row (16 lanes x 8 columns = 128 columns
+// per pass), so one warp instruction reads two full 256-byte att1 rows.
+// ---------------------------------------------------------------------------------------------
+inline size_t attn_alpha_smem_bytes(int L, int A, int KB) {
   const size_t Lp = (size_t)(L + 3) & ~(size_t)3;
-  return sizeof(float) * ((size_t)A + (size_t)KB * A + (size_t)KB * Lp +
-                          (size_t)(kAttnRowGroups - 1) * KB * kAttnDChunk) + sizeof(int) * 8;
+  return sizeof(float) * ((size_t)A + (size_t)KB * A + (size_t)KB * Lp);
 }
 
 template <typename ST, int KB>
-__global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnFwdArgs p) {
+__global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* w_s = reinterpret_cast<float*>(smem_raw);
   float* att2_s = w_s + p.A;                 // [KB][A]
-  float* e_s = att2_s + KB * p.A;            // [KB][L]
-  const int Lp = (p.L + 3) & ~3;             // row pitch of e_s (keeps part_s 16-byte aligned)
-  float* part_s = e_s + KB * Lp;             // [3][KB][DCH]
-  int* pos_s = reinterpret_cast<int*>(part_s + (kAttnRowGroups - 1) * KB * kAttnDChunk);
-
-  const int img = blockIdx.y;
-  const int d0 = blockIdx.x * kAttnDChunk;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* e_s = att2_s + KB * p.A;            // [KB][Lp]
   const int L = p.L, D = p.D, A = p.A;
+  const int Lp = (L + 3) & ~3;
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = img * KB;
 
-  for (int i = tid; i < A; i += kAttnThreads) w_s[i] = p.w_full[i];
-  for (int i = tid; i < KB * A; i += kAttnThreads) {
+  for (int i = tid; i < A; i += kAlphaThreads) w_s[i] = p.w_full[i];
+  for (int i = tid; i < KB * A; i += kAlphaThreads) {
     const int j = i / A, a = i - j * A;
     att2_s[i] = p.hp[(size_t)(row0 + j) * (A + D) + a];
   }
   __syncthreads();
 
-  // ---- phase 1: energies.  One warp per annotation row, lanes across A (4 columns each).
   const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)img * L * A;
   const float b_full = p.b_full[0];
-  for (int l = warp; l < L; l += kAttnThreads / 32) {
+  const int half = lane >> 4, hl = lane & 15;
+  constexpr int RPW = 2 * (kAlphaThreads / 32);      // rows per CTA pass (16)
+  for (int lb = 0; lb < L; lb += RPW) {
+    const int l = lb + warp * 2 + half;
     float acc[KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j) acc[j] = 0.f;
-    for (int a = lane * 4; a < A; a += 128) {
-      float v[4];
-      if (sizeof(ST) == 2) {
-        uint2 r = *reinterpret_cast<const uint2*>(att1 + (size_t)l * A + a);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-        float2 f0 = __bfloat1622float2(h2[0]), f1 = __bfloat1622float2(h2[1]);
-        v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
-      } else {
-        float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(att1) + (size_t)l * A + a);
-        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
-      }
+    if (l < L) {
+      for (int a = hl * 8; a < A; a += 128) {
+        float v[8];
+        if (a + 8 <= A) {
+          load8<ST>(att1 + (size_t)l * A + a, v);
+        } else {   // A % 8 == 4 tail
 #pragma unroll
-      for (int j = 0; j < KB; ++j) {
+          for (int q = 0; q < 8; ++q) v[q] = (a + q < A) ? to_f<ST>(att1[(size_t)l * A + a + q]) : 0.f;
+        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          acc[j] = fmaf(fmaxf(v[q] + att2_s[j * A + a + q], 0.f), w_s[a + q], acc[j]);
+        for (int j = 0; j < KB; ++j) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (a + q < A) acc[j] = fmaf(fmaxf(v[q] + att2_s[j * A + a + q], 0.f), w_s[a + q], acc[j]);
+        }
       }
     }
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
-      const float s = warp_sum(acc[j]);
-      if (lane == 0) e_s[j * Lp + l] = s + b_full;
+      float s = acc[j];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (hl == 0 && l < L) e_s[j * Lp + l] = s + b_full;
     }
   }
   __syncthreads();
 
-  // ---- phase 2: alpha.  Warp j normalises row j (KB <= 8 warps).
+  // normalisation: warp j owns row j (KB <= 8 warps)
   if (warp < KB) {
     const int j = warp;
     float* e = e_s + j * Lp;
@@ -121,7 +131,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnFwdAr
       }
       if (bi == 0x7fffffff) bi = 0;   // all NaN / -inf guard
       for (int l = lane; l < L; l += 32) e[l] = (l == bi) ? 1.f : 0.f;
-      if (lane == 0) pos_s[j] = bi;
     } else {
       float m = -INFINITY;
       for (int l = lane; l < L; l += 32) {
@@ -141,72 +150,119 @@ __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnFwdAr
       const float inv = 1.f / s;
       for (int l = lane; l < L; l += 32) e[l] *= inv;
     }
-    if (blockIdx.x == 0 && p.alpha_out) {
-      float* ao = p.alpha_out + (size_t)(row0 + j) * p.alpha_stride;
-      for (int l = lane; l < L; l += 32) ao[l] = e[l];
-    }
+    float* ao = p.alpha_out + (size_t)(row0 + j) * p.alpha_stride;
+    for (int l = lane; l < L; l += 32) ao[l] = e[l];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (b) context: the streaming pass over the annotations
+// ---------------------------------------------------------------------------------------------
+inline size_t attn_ctx_smem_bytes(int L, int KB) {
+  const size_t Lp = (size_t)(L + 3) & ~(size_t)3;
+  return sizeof(float) * ((size_t)KB * Lp + (size_t)(kCtxGroups - 1) * KB * kCtxCols) + 32;
+}
+
+template <typename ST, int KB>
+__global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int L = p.L, D = p.D, A = p.A;
+  const int Lp = (L + 3) & ~3;
+  float* al_s = reinterpret_cast<float*>(smem_raw);          // [KB][Lp]
+  float* part_s = al_s + KB * Lp;                            // [3][KB][256]
+  int* pos_s = reinterpret_cast<int*>(part_s + (kCtxGroups - 1) * KB * kCtxCols);
+
+  const int img = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
+  const int row0 = img * KB;
+  const int d = blockIdx.x * kCtxCols + lane * 8;
+  const bool active = d < D;
+  const ST* F = reinterpret_cast<const ST*>(p.F) + (size_t)img * L * D + d;
+
+  // first batch of annotation rows goes in flight before anything else is touched
+  Raw8<ST> v0[kCtxUnroll];
+  const bool gmax = p.mode == DIC_ATTN_GUMBEL_MAX;
+  const bool pre = active && !gmax && (rg + (kCtxUnroll - 1) * kCtxGroups < L);
+  if (pre) {
+#pragma unroll
+    for (int r = 0; r < kCtxUnroll; ++r) v0[r].load_stream(F + (size_t)(rg + r * kCtxGroups) * D);
+  }
+
+  for (int i = tid; i < KB * L; i += kCtxThreads) {
+    const int j = i / L, l = i - j * L;
+    const float a = p.alpha_out[(size_t)(row0 + j) * p.alpha_stride + l];
+    al_s[j * Lp + l] = a;
+    if (gmax && a == 1.f) pos_s[j] = l;
   }
   __syncthreads();
 
-  // ---- phase 3: context over this CTA's D chunk.  64 threads x 8 columns per row pass,
-  // 4 row groups; each thread keeps KB x 8 fp32 accumulators.
-  const int cg = tid & 63, rg = tid >> 6;
-  const int d = d0 + cg * 8;
-  const bool active = d < D;
   float acc[KB][8];
 #pragma unroll
   for (int j = 0; j < KB; ++j)
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[j][q] = 0.f;
 
-  const ST* F = reinterpret_cast<const ST*>(p.F) + (size_t)img * L * D;
   if (active) {
-    if (p.mode == DIC_ATTN_GUMBEL_MAX) {
-      // one-hot alpha: the weighted sum is a single-row gather (row group 0 only)
+    if (gmax) {
+      // one-hot alpha: the weighted sum is a single-row gather
       if (rg == 0) {
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
           float v[8];
-          load8<ST>(F + (size_t)pos_s[j] * D + d, v);
+          load8<ST>(F + (size_t)pos_s[j] * D, v);
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[j][q] = v[q];
         }
       }
     } else {
-      constexpr int UNR = 7;
       int l = rg;
-      for (; l + (UNR - 1) * kAttnRowGroups < L; l += UNR * kAttnRowGroups) {
-        float v[UNR][8];
+      if (pre) {
 #pragma unroll
-        for (int r = 0; r < UNR; ++r)
-          load8_stream<ST>(F + (size_t)(l + r * kAttnRowGroups) * D + d, v[r]);
-#pragma unroll
-        for (int r = 0; r < UNR; ++r) {
+        for (int r = 0; r < kCtxUnroll; ++r) {
+          float v[8];
+          v0[r].unpack(v);
 #pragma unroll
           for (int j = 0; j < KB; ++j) {
-            const float al = e_s[j * Lp + l + r * kAttnRowGroups];
+            const float al = al_s[j * Lp + l + r * kCtxGroups];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[j][q] = fmaf(al, v[r][q], acc[j][q]);
+            for (int q = 0; q < 8; ++q) acc[j][q] = fmaf(al, v[q], acc[j][q]);
+          }
+        }
+        l += kCtxUnroll * kCtxGroups;
+      }
+      for (; l + (kCtxUnroll - 1) * kCtxGroups < L; l += kCtxUnroll * kCtxGroups) {
+        Raw8<ST> raw[kCtxUnroll];
+#pragma unroll
+        for (int r = 0; r < kCtxUnroll; ++r) raw[r].load_stream(F + (size_t)(l + r * kCtxGroups) * D);
+#pragma unroll
+        for (int r = 0; r < kCtxUnroll; ++r) {
+          float v[8];
+          raw[r].unpack(v);
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+            const float al = al_s[j * Lp + l + r * kCtxGroups];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[j][q] = fmaf(al, v[q], acc[j][q]);
           }
         }
       }
-      for (; l < L; l += kAttnRowGroups) {
+      for (; l < L; l += kCtxGroups) {
         float v[8];
-        load8_stream<ST>(F + (size_t)l * D + d, v);
+        load8_stream<ST>(F + (size_t)l * D, v);
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
-          const float al = e_s[j * Lp + l];
+          const float al = al_s[j * Lp + l];
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[j][q] = fmaf(al, v[q], acc[j][q]);
         }
       }
     }
   }
-  // deterministic cross-group reduction: groups 1..3 park their partials, group 0 adds in order
+  // deterministic cross-warp reduction: warps 1..3 park their partials, warp 0 adds in order
   if (rg > 0) {
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
-      float* dst = part_s + ((size_t)(rg - 1) * KB + j) * kAttnDChunk + cg * 8;
+      float* dst = part_s + ((size_t)(rg - 1) * KB + j) * kCtxCols + lane * 8;
       *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
     }
@@ -216,8 +272,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnFwdAr
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
 #pragma unroll
-      for (int g = 0; g < kAttnRowGroups - 1; ++g) {
-        const float* src = part_s + ((size_t)g * KB + j) * kAttnDChunk + cg * 8;
+      for (int g = 0; g < kCtxGroups - 1; ++g) {
+        const float* src = part_s + ((size_t)g * KB + j) * kCtxCols + lane * 8;
         const float4 a = *reinterpret_cast<const float4*>(src);
         const float4 b = *reinterpret_cast<const float4*>(src + 4);
         acc[j][0] += a.x; acc[j][1] += a.y; acc[j][2] += a.z; acc[j][3] += a.w;
@@ -235,52 +291,59 @@ __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnFwdAr
   }
 }
 
-template <typename ST>
-inline int launch_attn_step(const AttnFwdArgs& p, int images, int KB, cudaStream_t st) {
-  if (images <= 0) return 0;
-  dim3 grid(cdiv(p.D, kAttnDChunk), images);
-  const size_t smem = attn_fwd_smem_bytes(p.L, p.A, KB);
-  // algorithmic bytes: annotations + att1 once per image-step
-  ProfScope prof(P_ATTN_FWD, st, (double)images * p.L * ((double)p.D + p.A) * sizeof(ST));
-#define DIC_ATTN_CASE(K)                                                                          \
-  case K: {                                                                                       \
-    static bool attr_set = false;                                                                 \
-    if (!attr_set) {                                                                              \
-      DIC_CUDA(cudaFuncSetAttribute(attn_step_kernel<ST, K>,                                      \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));    \
-      attr_set = true;                                                                            \
-    }                                                                                             \
-    attn_step_kernel<ST, K><<<grid, kAttnThreads, smem, st>>>(p);                                 \
-    break;                                                                                        \
+template <typename ST, int KB>
+inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIC_CUDA(cudaFuncSetAttribute(attn_alpha_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DIC_CUDA(cudaFuncSetAttribute(attn_context_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
   }
-  switch (KB) {
-    DIC_ATTN_CASE(1)
-    DIC_ATTN_CASE(2)
-    DIC_ATTN_CASE(3)
-    DIC_ATTN_CASE(4)
-    DIC_ATTN_CASE(5)
-    DIC_ATTN_CASE(6)
-    DIC_ATTN_CASE(7)
-    DIC_ATTN_CASE(8)
-    default:
-      DIC_FAIL(-4, "attn_step: rows per image %d not in 1..8", KB);
+  {
+    ProfScope prof(P_ATTN_ALPHA, st, (double)images * p.L * p.A * sizeof(ST));
+    attn_alpha_kernel<ST, KB><<<images, kAlphaThreads, attn_alpha_smem_bytes(p.L, p.A, KB), st>>>(p);
+    DIC_LAUNCH_CHECK();
   }
-#undef DIC_ATTN_CASE
-  DIC_LAUNCH_CHECK();
+  {
+    // algorithmic bytes of the context pass: the annotations once per image-step
+    ProfScope prof(P_ATTN_FWD, st, (double)images * p.L * (double)p.D * sizeof(ST));
+    dim3 grid(cdiv(p.D, kCtxCols), images);
+    attn_context_kernel<ST, KB><<<grid, kCtxThreads, attn_ctx_smem_bytes(p.L, KB), st>>>(p);
+    DIC_LAUNCH_CHECK();
+  }
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// Backward of one attention step (training, one row per image).
-//   dz      = dzg * beta                  -> DZ (ST), consumed post-loop by dF += alpha^T dz
-//   dbeta'  = dzg * z * beta (1-beta)     -> G[:, gcol_beta + d]     (ST)
-//   dalpha  = F . dz (+ external d_alphas)            (second pass over the annotations)
-//   de      = alpha * (dalpha - sum alpha dalpha) * inv_temp         -> de_out
-//   datt2   = w * sum_l de[l] 1[pre>0]    -> G[:, gcol_att2 + a]     (ST)
-//   dw_full partial = sum_l de[l] relu(pre[l,:]) ; db_full partial = sum_l de[l]
-// ------------------------------------------------------------------------------------------
-constexpr int kAttnBwdThreads = 512;
+template <typename ST>
+inline int launch_attn_step(const AttnFwdArgs& p, int images, int KB, cudaStream_t st) {
+  if (images <= 0) return 0;
+  if (!p.alpha_out) DIC_FAIL(-4, "attn_step: alpha buffer is required");
+  switch (KB) {
+    case 1: return launch_attn_step_kb<ST, 1>(p, images, st);
+    case 2: return launch_attn_step_kb<ST, 2>(p, images, st);
+    case 3: return launch_attn_step_kb<ST, 3>(p, images, st);
+    case 4: return launch_attn_step_kb<ST, 4>(p, images, st);
+    case 5: return launch_attn_step_kb<ST, 5>(p, images, st);
+    case 6: return launch_attn_step_kb<ST, 6>(p, images, st);
+    case 7: return launch_attn_step_kb<ST, 7>(p, images, st);
+    case 8: return launch_attn_step_kb<ST, 8>(p, images, st);
+    default: DIC_FAIL(-4, "attn_step: rows per image %d not in 1..8", KB);
+  }
+}
 
+// ------------------------------------------------------------------------------------------
+// Backward of one attention step (training, one row per image), again split into the streaming
+// pass over the annotations and a small per-image kernel:
+//   (a) attn_bwd_stream_kernel, grid (D/256, rows):
+//         dz      = dzg * beta                -> DZ (ST), consumed post-loop by dF += alpha^T dz
+//         dbeta'  = dzg * z * beta (1-beta)   -> G[:, gcol_beta + d]     (ST)
+//         dalpha partial[chunk][b][l] = F[l, chunk] . dz[chunk]
+//   (b) attn_bwd_small_kernel, one CTA per image:
+//         dalpha  = sum_chunks partial (+ external d_alphas)
+//         de      = alpha * (dalpha - sum alpha dalpha) * inv_temp       -> de_out
+//         datt2   = w * sum_l de[l] 1[pre>0]  -> G[:, gcol_att2 + a]     (ST)
+//         dw_full partial = sum_l de[l] relu(pre[l,:]) ; db_full partial = sum_l de[l]
+// ------------------------------------------------------------------------------------------
 struct AttnBwdArgs {
   const void* F;         // [B, L, D] ST
   const void* att1;      // [B, L, A] ST
@@ -298,104 +361,170 @@ struct AttnBwdArgs {
   float* de_out;         // [B, L]
   float* dwfull_part;    // [B, A]
   float* dbfull_part;    // [B]
+  float* dal_part;       // [chunks][part_rows][L] fp32 scratch
+  int part_rows;
   int L, D, A;
   float inv_temp;
 };
 
-inline size_t attn_bwd_smem_bytes(int L, int D, int A) {
-  // dz[D] | dal[L] | al[L] | w[A] | att2[A] | red[2][4][A] | scratch[64]
-  return sizeof(float) * ((size_t)D + 2 * (size_t)L + 2 * (size_t)A + 8 * (size_t)A + 64);
+template <typename ST>
+__global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const AttnBwdArgs p) {
+  const int L = p.L, D = p.D, A = p.A;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
+  const int d = chunk * kCtxCols + lane * 8;
+  const bool active = d < D;
+  const ST* F = reinterpret_cast<const ST*>(p.F) + (size_t)b * L * D + d;
+  float* part = p.dal_part + ((size_t)chunk * p.part_rows + b) * L;
+
+  // `pre` is warp-uniform (rg is the warp index): the blocks below contain warp shuffles
+  Raw8<ST> v0[kCtxUnroll];
+  const bool pre = (rg + (kCtxUnroll - 1) * kCtxGroups < L);
+  if (pre) {
+#pragma unroll
+    for (int r = 0; r < kCtxUnroll; ++r) {
+      if (active) v0[r].load_stream(F + (size_t)(rg + r * kCtxGroups) * D);
+      else v0[r].zero();
+    }
+  }
+
+  float dz[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dz[q] = 0.f;
+  if (active) {
+    float beta[8], g[8], zz[8];
+    load8<float>(p.hp + (size_t)b * (A + D) + A + d, beta);
+    load8<float>(p.dzg + (size_t)b * D + d, g);
+    load8<float>(p.z + (size_t)b * D + d, zz);
+    float db[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      dz[q] = g[q] * beta[q];
+      db[q] = g[q] * zz[q] * beta[q] * (1.f - beta[q]);
+    }
+    if (rg == 0) {
+      store8<ST>(reinterpret_cast<ST*>(p.DZ) + (size_t)b * D + d, dz);
+      store8<ST>(reinterpret_cast<ST*>(p.G) + (size_t)b * p.g_stride + p.gcol_beta + d, db);
+    }
+  }
+
+  int l = rg;
+  if (pre) {
+#pragma unroll
+    for (int r = 0; r < kCtxUnroll; ++r) {
+      float v[8];
+      v0[r].unpack(v);
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s = fmaf(v[q], dz[q], s);
+      s = warp_sum(s);
+      if (lane == 0) part[l + r * kCtxGroups] = s;
+    }
+    l += kCtxUnroll * kCtxGroups;
+  }
+  for (; l + (kCtxUnroll - 1) * kCtxGroups < L; l += kCtxUnroll * kCtxGroups) {
+    Raw8<ST> raw[kCtxUnroll];
+#pragma unroll
+    for (int r = 0; r < kCtxUnroll; ++r) {
+      if (active) raw[r].load_stream(F + (size_t)(l + r * kCtxGroups) * D);
+      else raw[r].zero();
+    }
+#pragma unroll
+    for (int r = 0; r < kCtxUnroll; ++r) {
+      float v[8];
+      raw[r].unpack(v);
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s = fmaf(v[q], dz[q], s);
+      s = warp_sum(s);
+      if (lane == 0) part[l + r * kCtxGroups] = s;
+    }
+  }
+  for (; l < L; l += kCtxGroups) {
+    float s = 0.f;
+    if (active) {
+      float v[8];
+      load8_stream<ST>(F + (size_t)l * D, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s = fmaf(v[q], dz[q], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) part[l] = s;
+  }
+}
+
+constexpr int kBwdSmallThreads = 256;
+
+inline size_t attn_bwd_small_smem_bytes(int L, int A) {
+  // de[L] | al[L] | w[A] | att2[A] | red[2][2][A] | scratch[64]
+  return sizeof(float) * (2 * (size_t)L + 2 * (size_t)A + 4 * (size_t)A + 64);
 }
 
 template <typename ST>
-__global__ void __launch_bounds__(kAttnBwdThreads) attn_bwd_kernel(const AttnBwdArgs p) {
+__global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const AttnBwdArgs p, int chunks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = p.L, D = p.D, A = p.A;
-  float* dz_s = reinterpret_cast<float*>(smem_raw);
-  float* dal_s = dz_s + D;
-  float* al_s = dal_s + L;
+  float* de_s = reinterpret_cast<float*>(smem_raw);
+  float* al_s = de_s + L;
   float* w_s = al_s + L;
   float* att2_s = w_s + A;
-  float* red_s = att2_s + A;       // [2][4][A]
-  float* scratch = red_s + 8 * A;  // 64
-
+  float* red_s = att2_s + A;       // [2][2][A]
+  float* scratch = red_s + 4 * A;  // 64
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const float* hp = p.hp + (size_t)b * (A + D);
   ST* G = reinterpret_cast<ST*>(p.G) + (size_t)b * p.g_stride;
 
-  for (int d = tid; d < D; d += kAttnBwdThreads) {
-    const float beta = hp[A + d];
-    const float g = p.dzg[(size_t)b * D + d];
-    const float zz = p.z[(size_t)b * D + d];
-    const float dz = g * beta;
-    dz_s[d] = dz;
-    reinterpret_cast<ST*>(p.DZ)[(size_t)b * D + d] = from_f<ST>(dz);
-    G[p.gcol_beta + d] = from_f<ST>(g * zz * beta * (1.f - beta));
-  }
-  for (int a = tid; a < A; a += kAttnBwdThreads) {
+  for (int a = tid; a < A; a += kBwdSmallThreads) {
     w_s[a] = p.w_full[a];
     att2_s[a] = hp[a];
   }
-  for (int l = tid; l < L; l += kAttnBwdThreads) al_s[l] = p.alpha[(size_t)b * p.alpha_stride + l];
-  __syncthreads();
-
-  // dalpha[l] = F[l,:] . dz  -- one warp per annotation row, 16-byte loads
-  const ST* F = reinterpret_cast<const ST*>(p.F) + (size_t)b * L * D;
-  for (int l = warp; l < L; l += kAttnBwdThreads / 32) {
-    float s = 0.f;
-    for (int d = lane * 8; d < D; d += 256) {
-      float v[8];
-      load8_stream<ST>(F + (size_t)l * D + d, v);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) s = fmaf(v[q], dz_s[d + q], s);
-    }
-    s = warp_sum(s);
-    if (lane == 0) {
-      if (p.dalpha) s += p.dalpha[(size_t)b * p.alpha_stride + l];
-      dal_s[l] = s;
-    }
-  }
-  __syncthreads();
-
-  // softmax backward
   float part = 0.f;
-  for (int l = tid; l < L; l += kAttnBwdThreads) part += al_s[l] * dal_s[l];
+  for (int l = tid; l < L; l += kBwdSmallThreads) {
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += p.dal_part[((size_t)c * p.part_rows + b) * L + l];
+    if (p.dalpha) s += p.dalpha[(size_t)b * p.alpha_stride + l];
+    const float al = p.alpha[(size_t)b * p.alpha_stride + l];
+    al_s[l] = al;
+    de_s[l] = s;         // dalpha for now
+    part += al * s;
+  }
   const float dot = block_sum(part, scratch);
   float desum = 0.f;
-  for (int l = tid; l < L; l += kAttnBwdThreads) {
-    const float de = al_s[l] * (dal_s[l] - dot) * p.inv_temp;
-    dal_s[l] = de;  // reuse as de
+  for (int l = tid; l < L; l += kBwdSmallThreads) {
+    const float de = al_s[l] * (de_s[l] - dot) * p.inv_temp;
+    de_s[l] = de;
     p.de_out[(size_t)b * L + l] = de;
     desum += de;
   }
-  const float dbf = block_sum(desum, scratch);  // includes the __syncthreads that publishes de
+  const float dbf = block_sum(desum, scratch);   // its barriers also publish de_s
   if (tid == 0) p.dbfull_part[b] = dbf;
 
-  // relu mask pass over att1: thread (a, row group)
+  // relu-mask pass over att1: thread (column a, row group)
   const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)b * L * A;
-  const int rg = tid >> 7, a0 = tid & 127;   // 4 row groups x 128 columns
+  const int rg = tid >> 7, a0 = tid & 127;   // 2 row groups x 128 columns
   for (int ab = 0; ab < A; ab += 128) {
     const int a = ab + a0;
-    float s1 = 0.f, s2 = 0.f;
     if (a < A) {
       const float a2 = att2_s[a];
-      for (int l = rg; l < L; l += 4) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+      for (int l = rg; l < L; l += 2) {
         const float pre = to_f<ST>(att1[(size_t)l * A + a]) + a2;
         if (pre > 0.f) {
-          const float de = dal_s[l];
+          const float de = de_s[l];
           s1 += de;
           s2 = fmaf(de, pre, s2);
         }
       }
-      red_s[(0 * 4 + rg) * A + a] = s1;
-      red_s[(1 * 4 + rg) * A + a] = s2;
+      red_s[(0 * 2 + rg) * A + a] = s1;
+      red_s[(1 * 2 + rg) * A + a] = s2;
     }
   }
   __syncthreads();
-  for (int a = tid; a < A; a += kAttnBwdThreads) {
-    const float s1 = red_s[0 * A + a] + red_s[1 * A + a] + red_s[2 * A + a] + red_s[3 * A + a];
-    const float s2 = red_s[4 * A + a] + red_s[5 * A + a] + red_s[6 * A + a] + red_s[7 * A + a];
+  for (int a = tid; a < A; a += kBwdSmallThreads) {
+    const float s1 = red_s[0 * A + a] + red_s[1 * A + a];
+    const float s2 = red_s[2 * A + a] + red_s[3 * A + a];
     G[p.gcol_att2 + a] = from_f<ST>(w_s[a] * s1);
     p.dwfull_part[(size_t)b * A + a] = s2;
   }
@@ -404,16 +533,23 @@ __global__ void __launch_bounds__(kAttnBwdThreads) attn_bwd_kernel(const AttnBwd
 template <typename ST>
 inline int launch_attn_bwd(const AttnBwdArgs& p, int rows, cudaStream_t st) {
   if (rows <= 0) return 0;
-  const size_t smem = attn_bwd_smem_bytes(p.L, p.D, p.A);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DIC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  200 * 1024));
-    attr_set = true;
+  const int chunks = cdiv(p.D, kCtxCols);
+  {
+    ProfScope prof(P_ATTN_BWD, st, (double)rows * p.L * (double)p.D * sizeof(ST));
+    dim3 grid(chunks, rows);
+    attn_bwd_stream_kernel<ST><<<grid, kCtxThreads, 0, st>>>(p);
+    DIC_LAUNCH_CHECK();
   }
-  ProfScope prof(P_ATTN_BWD, st, (double)rows * p.L * ((double)p.D + p.A) * sizeof(ST));
-  attn_bwd_kernel<ST><<<rows, kAttnBwdThreads, smem, st>>>(p);
-  DIC_LAUNCH_CHECK();
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DIC_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    ProfScope prof(P_ATTN_BWD_SMALL, st, (double)rows * p.L * p.A * sizeof(ST));
+    attn_bwd_small_kernel<ST><<<rows, kBwdSmallThreads, attn_bwd_small_smem_bytes(p.L, p.A), st>>>(p, chunks);
+    DIC_LAUNCH_CHECK();
+  }
   return 0;
 }
 

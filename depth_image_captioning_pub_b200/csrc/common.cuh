@@ -49,10 +49,14 @@ extern thread_local char g_err[512];
 // (bench.py reads these through dic_launch_count / dic_profile_*; off by default, no cost)
 inline std::atomic<long long> g_launches{0};
 
-enum ProfClass { P_ATTN_FWD = 0, P_ATTN_BWD, P_DATT1, P_GEMM_TC, P_GEMM_FMA, P_LSTM, P_FUSE, P_COLSUM, P_N };
+enum ProfClass {
+  P_ATTN_FWD = 0, P_ATTN_BWD, P_DATT1, P_GEMM_TC, P_GEMM_FMA, P_LSTM, P_FUSE, P_COLSUM,
+  P_ATTN_ALPHA, P_ATTN_BWD_SMALL, P_DFEAT, P_N
+};
 inline const char* prof_class_name(int c) {
-  static const char* names[P_N] = {"attn_step_fwd", "attn_step_bwd", "datt1", "gemm_tcgen05",
-                                   "gemm_fma", "lstm_pointwise", "fuse_feats", "colsum"};
+  static const char* names[P_N] = {"attn_context_fwd", "attn_stream_bwd", "datt1", "gemm_tcgen05",
+                                   "gemm_fma", "lstm_pointwise", "fuse_feats", "colsum",
+                                   "attn_alpha_fwd", "attn_small_bwd", "dfeat_accumulate"};
   return (c >= 0 && c < P_N) ? names[c] : "?";
 }
 struct ProfState {
@@ -161,6 +165,44 @@ __device__ __forceinline__ void load8_stream<bf16>(const bf16* p, float (&v)[8])
     v[2 * i + 1] = f.y;
   }
 }
+
+// Raw (unconverted) 8-element vectors: streaming kernels keep several of these in flight per
+// thread; holding bf16 data packed (4 registers instead of 8) is what lets 8+ CTAs fit per SM.
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load_stream(const bf16* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  }
+  __device__ __forceinline__ void zero() { r = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load_stream(const float* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4));
+  }
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
 
 template <typename T>
 __device__ __forceinline__ void store8(T* p, const float (&v)[8]);

@@ -90,16 +90,16 @@ static int prologue(const dic_dims& d, const Pack& pk, const void* f_rgb, const 
 }
 
 template <typename ST>
-static int init_state_gemm(const dic_dims& d, const Pack& pk, const float* meanF, int B, void* h_out,
-                           int h_bf16, long long h_ld, float* c_out, cudaStream_t st) {
+static int init_state_gemm(const dic_dims& d, const Pack& pk, const float* meanF, int B, float* h0,
+                           float* c0, cudaStream_t st) {
   const int is_bf16 = sizeof(ST) == 2;
-  // h0, c0 = chunk(init_linear(mean_l F), 2)   (depth_models.py:166-168)
-  GemmArgs g = gemm_args_nt(meanF, 0, d.D, pk.Winit(), is_bf16, d.D, h_out, h_bf16, h_ld, B, d.H, d.D,
-                            pk.b_init());
-  DIC_TRY(gemm_generic(g, st));
+  // h0, c0 = chunk(init_linear(mean_l F), 2)   (depth_models.py:166-168); dense fp32 [B,H] outputs,
+  // K = D is long and the output tiny, so the contraction is split across the SMs
+  GemmArgs g = gemm_args_nt(meanF, 0, d.D, pk.Winit(), is_bf16, d.D, h0, 0, d.H, B, d.H, d.D, pk.b_init());
+  DIC_TRY(gemm_splitk(g, st));
   const char* w2 = reinterpret_cast<const char*>(pk.Winit()) + (size_t)d.H * d.D * sizeof(ST);
-  g = gemm_args_nt(meanF, 0, d.D, w2, is_bf16, d.D, c_out, 0, d.H, B, d.H, d.D, pk.b_init() + d.H);
-  DIC_TRY(gemm_generic(g, st));
+  g = gemm_args_nt(meanF, 0, d.D, w2, is_bf16, d.D, c0, 0, d.H, B, d.H, d.D, pk.b_init() + d.H);
+  DIC_TRY(gemm_splitk(g, st));
   return 0;
 }
 
@@ -164,7 +164,11 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
 
   const ST* F = nullptr;
   DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, att1, &F, st));
-  DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, XH + d.E + d.D, is_bf16, (long long)XW, c_all, st));
+  {
+    float* h0 = reinterpret_cast<float*>(ws + lay.h0);
+    DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, h0, c_all, st));
+    DIC_TRY(launch_copy2d(h0, d.H, XH + d.E + d.D, (long long)XW, is_bf16, B, d.H, st));
+  }
 
   // all-step embedding gather (depth_models.py:160)
   {
@@ -313,7 +317,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
       GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, reinterpret_cast<const ST*>(pk.Wg()) + E, is_bf16, 0, dzg,
                                 0, D, n, D, 4 * H, nullptr);
       g.b_n = 1; g.b_k = XW;
-      DIC_TRY(gemm(g, st));
+      DIC_TRY(gemm_splitk(g, st));
     }
 
     AttnBwdArgs ab;
@@ -328,6 +332,8 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     ab.de_out = de + (size_t)t * B * L;
     ab.dwfull_part = dwfull_part + (size_t)t * B * A;
     ab.dbfull_part = dbfull_part + (size_t)t * B;
+    ab.dal_part = reinterpret_cast<float*>(ws + lay.dal_part);
+    ab.part_rows = B;
     ab.L = L; ab.D = D; ab.A = A; ab.inv_temp = inv_temp;
     DIC_TRY(launch_attn_bwd<ST>(ab, n, st));
 
@@ -335,7 +341,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     {
       GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, pk.Whdb(), is_bf16, 0, dh, 0, H, n, H, (int)GW, nullptr);
       g.b_n = 1; g.b_k = H;
-      DIC_TRY(gemm(g, st));
+      DIC_TRY(gemm_splitk(g, st));   // zero-fills and accumulates only the n valid rows
     }
   }
 
@@ -412,14 +418,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     GemmArgs g = gemm_args_nt(datt1, is_bf16, A, pk.Wenc(), is_bf16, 0, d_feats, 0, D, B * L, D, A, nullptr);
     g.b_n = 1; g.b_k = D;
     DIC_TRY(gemm(g, st));
-    GemmArgs g2 = gemm_args_nt(alphas, 0, 0, DZ, is_bf16, 0, d_feats, 0, D, L, D, T, dmeanF);
-    g2.a_m = 1; g2.a_k = L; g2.a_batch = (long long)T * L;
-    g2.b_n = 1; g2.b_k = (long long)B * D; g2.b_batch = D;
-    g2.c_batch = (long long)L * D;
-    g2.bias_batch = D; g2.bias_scale = 1.f / (float)L;
-    g2.batch = B;
-    g2.accumulate = 1;
-    DIC_TRY(gemm_generic(g2, st));
+    DIC_TRY(launch_dfeat_accumulate<ST>(d_feats, alphas, DZ, dmeanF, B, L, D, T, 1, st));
   }
   return 0;
 }
@@ -461,7 +460,7 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
 
   const ST* F = nullptr;
   DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, att1, &F, st));
-  DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, h0, 0, H, c0, st));
+  DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, h0, c0, st));
   DIC_CUDA(cudaMemsetAsync(XH, 0, (size_t)2 * R * XW * sizeof(ST), st));
   decode_init_kernel<ST><<<cdiv(R * (E + H), 256), 256, 0, st>>>(
       h0, c0, reinterpret_cast<const ST*>(pk.Emb()), start_id, XH, XW, E + D, c, R, K, E, H);
@@ -480,7 +479,7 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
     memset(&a, 0, sizeof(a));
     a.F = F; a.att1 = att1; a.hp = HP; a.w_full = pk.w_full(); a.b_full = pk.b_full();
     a.u = u ? u + (size_t)t * R * L : nullptr;
-    a.alpha_out = alphas_out ? alphas_out + (size_t)t * R * L : nullptr;
+    a.alpha_out = alphas_out ? alphas_out + (size_t)t * R * L : reinterpret_cast<float*>(ws + lay.alpha);
     a.alpha_stride = L;
     a.z_out = nullptr;
     a.zg_out = X + E; a.zg_stride = XW;

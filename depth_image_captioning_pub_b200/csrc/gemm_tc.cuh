@@ -1,17 +1,23 @@
 // tcgen05 + TMA GEMM engine for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 //
-//   C[M,N] = act( A[M,K] . B[N,K]^T (+ bias[N]) )        A, B K-major ("TN")
+//   C[M,N] = act( A . B^T (+ bias[N]) ),  A(m,k), B(n,k) each K-major or MN-major in global memory
 //
-// One 128 x BN output tile per CTA.  Warp-specialised:
-//   warp 0  : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
-//   warp 1  : MMA issuer    (one elected thread, tcgen05.mma.cta_group::1.kind::f16, UMMA 128xBNx16)
-//   warp 2  : TMEM allocator
-//   warps 4-7: epilogue     (tcgen05.ld 32x32b -> bias / sigmoid / cast -> global)
-// Out-of-range rows/columns/K are zero-filled by TMA, so no tail special cases in the main loop.
-// Split-K over gridDim.z: atomic fp32 accumulation or per-split partial buffers (GemmArgs).
+// Persistent, warp-specialised kernel: one CTA per SM walks the (split, m, n) tile list.
+//   warp 0    : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring that keeps
+//               running across tiles)
+//   warp 1    : MMA issuer    (one elected thread, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16,
+//               two TMEM accumulator stages so tile i+1 is computed while tile i drains)
+//   warp 2    : TMEM allocator (2*BN columns)
+//   warps 4-11: epilogue      (tcgen05.ld 32x32b -> bias / sigmoid / cast -> global; the TMEM stage is
+//               released as soon as the accumulator is in registers, before the global stores)
+// Out-of-range rows/columns/K are zero-filled by TMA, so there are no tail cases in the main loop.
+// Split-K: atomic fp32 accumulation or per-split partial buffers (GemmArgs.split_mode).
 //
-// Descriptor encodings follow the PTX ISA tcgen05 matrix/instruction descriptor tables
-// (cross-checked with cute/arch/mma_sm100_desc.hpp field layouts).
+// Operand layouts (DESIGN.md "GEMM engine"):
+//   K-major  : row-major [MN, K]; TMA box = 64 K-elements (128 B) x rows; UMMA desc SBO = 1024 B
+//   MN-major : row-major [K, MN]; TMA box = 64 MN-elements (128 B) x 64 K rows per 64-wide MN block;
+//              UMMA desc SBO = 1024 B (next 8 K rows), LBO = 8192 B (next 64-wide MN block)
+// Descriptor field layouts follow the PTX ISA tcgen05 tables (cf. cute/arch/mma_sm100_desc.hpp).
 #pragma once
 #include <cuda.h>
 
@@ -22,8 +28,9 @@ namespace dic {
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 64;       // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kTcStages = 4;
-constexpr int kTcThreads = 256;
-constexpr uint32_t kSpinLimit = 1u << 26;   // turn a would-be hang into a trap
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = 128 + 32 * kTcEpiWarps;   // 384
+constexpr uint32_t kSpinLimit = 1u << 27;            // turn a would-be hang into a trap
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -34,6 +41,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -113,8 +123,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct TcArgs {
   void* C;
@@ -126,6 +136,7 @@ struct TcArgs {
   long long split_stride;
   float alpha;
   int sig_lo, sig_hi;
+  int tiles_m, tiles_n;
 };
 
 template <int BN>
@@ -136,26 +147,27 @@ constexpr size_t tc_smem_bytes() {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+  static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
+  static_assert(!B_MN || BN >= 64, "MN-major B needs whole 64-wide blocks");
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = kTcBM * kTcBK * 2;
   constexpr uint32_t B_BYTES = BN * kTcBK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;              // two accumulator stages (64/128/256: powers of 2)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + kTcStages * STAGE_BYTES;
-  // barriers: full[s] at +8*s, empty[s] at +8*(S+s), tmem_full at +8*2S, tmem ptr slot after
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kTcStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kTcStages + 1);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kTcStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kTcStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kTcStages + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
-  const int split = blockIdx.z;
   const int num_kb = (p.K + kTcBK - 1) / kTcBK;
-  const int kb0 = (int)(((long long)num_kb * split) / p.splits);
-  const int kb1 = (int)(((long long)num_kb * (split + 1)) / p.splits);
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total = tiles_mn * p.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -166,11 +178,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kTcEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -178,30 +193,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // tile index -> (split, m block, n block); n fastest so that concurrent CTAs share the A tile in L2
+  auto decode = [&](int t, int& split, int& m0, int& n0, int& kb0, int& kb1) {
+    split = t / tiles_mn;
+    const int r = t - split * tiles_mn;
+    m0 = (r / p.tiles_n) * kTcBM;
+    n0 = (r % p.tiles_n) * BN;
+    kb0 = (int)(((long long)num_kb * split) / p.splits);
+    kb1 = (int)(((long long)num_kb * (split + 1)) / p.splits);
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-        if (A_MN) {
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int split, m0, n0, kb0, kb1;
+        decode(t, split, m0, n0, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (A_MN) {
 #pragma unroll
-          for (int h = 0; h < kTcBM / 64; ++h)
-            tma_load_2d(sa + h * (kTcBK * 128), &tmA, full_bar(stage), m0 + 64 * h, kb * kTcBK);
-        } else {
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * kTcBK, m0);
-        }
-        if (B_MN) {
+            for (int h = 0; h < kTcBM / 64; ++h)
+              tma_load_2d(sa + h * (kTcBK * 128), &tmA, full_bar(stage), m0 + 64 * h, kb * kTcBK);
+          } else {
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * kTcBK, m0);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int h = 0; h < BN / 64; ++h)
-            tma_load_2d(sb + h * (kTcBK * 128), &tmB, full_bar(stage), n0 + 64 * h, kb * kTcBK);
-        } else {
-          tma_load_2d(sb, &tmB, full_bar(stage), kb * kTcBK, n0);
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sb + h * (kTcBK * 128), &tmB, full_bar(stage), n0 + 64 * h, kb * kTcBK);
+          } else {
+            tma_load_2d(sb, &tmB, full_bar(stage), kb * kTcBK, n0);
+          }
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
-        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -214,76 +243,108 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t b_kstep = B_MN ? (16 * 128) >> 4 : 32 >> 4;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int split, m0, n0, kb0, kb1;
+        decode(t, split, m0, n0, kb0, kb1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);     // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        const uint64_t adesc = A_MN ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
-        const uint64_t bdesc = B_MN ? umma_desc_mnmajor_sw128(sb) : umma_desc_kmajor_sw128(sb);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t adesc = A_MN ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = B_MN ? umma_desc_mnmajor_sw128(sb) : umma_desc_kmajor_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < kTcBK / 16; ++k) {
-          umma_bf16(tmem_base, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kTcBK / 16; ++k) {
+            umma_bf16(tmem_d, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
-        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        umma_commit(tfull_bar(acc));       // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
-    const int q = warp & 3;               // TMEM lane quadrant of this warp
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
-    char* Cb = reinterpret_cast<char*>(p.C);
-    size_t cbase = (size_t)m * p.ldc;
-    if (p.splits > 1 && p.split_mode == 1) cbase += (size_t)split * p.split_stride;
-    const bool atomic = p.splits > 1 && p.split_mode == 0;
-    const bool add_bias = p.bias != nullptr && split == 0;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      if (m < p.M) {
-        const int nb = n0 + c;
-        float v[32];
+    const int ew = warp - 4;
+    const int q = warp & 3;                           // TMEM lane quadrant this warp may read
+    constexpr int GROUPS = BN >= 64 ? 2 : 1;          // column halves handled by different warps
+    constexpr int COLS = BN / GROUPS;
+    const int grp = ew >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      int split, m0, n0, kb0, kb1;
+      decode(t, split, m0, n0, kb0, kb1);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[COLS / 32][32];
+      if (grp < GROUPS) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) * p.alpha;
-          const int n = nb + j;
-          if (add_bias && n < p.N) x += p.bias[n];
-          if (n >= p.sig_lo && n < p.sig_hi) x = sigmoidf_acc(x);
-          v[j] = x;
-        }
-        if (atomic) {
+        for (int c = 0; c < COLS / 32; ++c)
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + grp * COLS + c * 32), r[c]);
+        tmem_ld_wait();
+      }
+      // accumulator is in registers: hand the TMEM stage back before touching global memory
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      const int m = m0 + q * 32 + lane;
+      if (grp < GROUPS && m < p.M) {
+        char* Cb = reinterpret_cast<char*>(p.C);
+        size_t cbase = (size_t)m * p.ldc;
+        if (p.splits > 1 && p.split_mode == 1) cbase += (size_t)split * p.split_stride;
+        const bool atomic = p.splits > 1 && p.split_mode == 0;
+        const bool add_bias = p.bias != nullptr && split == 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) atomicAdd(reinterpret_cast<float*>(Cb) + cbase + nb + j, v[j]);
-        } else if (p.c_bf16) {
-          bf16* dst = reinterpret_cast<bf16*>(Cb) + cbase + nb;
-          if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        for (int c = 0; c < COLS / 32; ++c) {
+          const int nb = n0 + grp * COLS + c * 32;
+          if (nb >= p.N) continue;
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float t8[8];
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[c][j]) * p.alpha;
+            const int n = nb + j;
+            if (add_bias && n < p.N) x += p.bias[n];
+            if (n >= p.sig_lo && n < p.sig_hi) x = sigmoidf_acc(x);
+            v[j] = x;
+          }
+          if (atomic) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) t8[e] = v[j + e];
-              store8<bf16>(dst + j, t8);
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) atomicAdd(reinterpret_cast<float*>(Cb) + cbase + nb + j, v[j]);
+          } else if (p.c_bf16) {
+            bf16* dst = reinterpret_cast<bf16*>(Cb) + cbase + nb;
+            if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t8[e] = v[j + e];
+                store8<bf16>(dst + j, t8);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
             }
           } else {
+            float* dst = reinterpret_cast<float*>(Cb) + cbase + nb;
+            if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
-          }
-        } else {
-          float* dst = reinterpret_cast<float*>(Cb) + cbase + nb;
-          if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) dst[j] = v[j];
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) dst[j] = v[j];
+            }
           }
         }
       }
@@ -293,7 +354,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -343,6 +404,17 @@ inline bool tc_enabled() {
   return v == 1;
 }
 
+inline int tc_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 // operand layouts the engine takes: K-major (k stride 1) or MN-major (m/n stride 1); the other
 // stride must keep TMA's 16-byte global stride rule
 inline bool tc_operand_ok(const void* p, long long s_mn, long long s_k) {
@@ -364,7 +436,7 @@ inline bool tc_gemm_eligible(const GemmArgs& g) {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& p, dim3 grid,
+inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& p, int grid,
                           cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -377,8 +449,8 @@ inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return 0;
 }
 
-inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
-  constexpr int BN = 128;
+template <int BN>
+inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   const bool a_mn = g.a_k != 1, b_mn = g.b_k != 1;
   CUtensorMap tmA, tmB;
   // K-major: matrix [MN rows, K cols], box MN x 64(K).  MN-major: matrix [K rows, MN cols], box 64(K) x 64(MN).
@@ -395,12 +467,32 @@ inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
     DIC_FAIL(-4, "tc_gemm: partial-buffer split-K needs splits <= K/64");
   p.split_mode = g.split_mode; p.split_stride = g.split_stride;
   p.alpha = g.alpha; p.sig_lo = g.sig_lo; p.sig_hi = g.sig_hi;
-  dim3 grid(cdiv(g.N, BN), cdiv(g.M, kTcBM), p.splits);
+  p.tiles_m = cdiv(g.M, kTcBM);
+  p.tiles_n = cdiv(g.N, BN);
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
+  const int grid = (int)(total < tc_num_sms() ? total : tc_num_sms());
   ProfScope prof(P_GEMM_TC, st);
-  if (!a_mn && !b_mn) return tc_gemm_launch<BN, false, false>(tmA, tmB, p, grid, st);
-  if (!a_mn && b_mn) return tc_gemm_launch<BN, false, true>(tmA, tmB, p, grid, st);
-  if (a_mn && !b_mn) return tc_gemm_launch<BN, true, false>(tmA, tmB, p, grid, st);
-  return tc_gemm_launch<BN, true, true>(tmA, tmB, p, grid, st);
+  if constexpr (BN >= 64) {
+    if (!a_mn && b_mn) return tc_gemm_launch<BN, false, true>(tmA, tmB, p, grid, st);
+    if (a_mn && b_mn) return tc_gemm_launch<BN, true, true>(tmA, tmB, p, grid, st);
+  }
+  if (a_mn) return tc_gemm_launch<BN, true, false>(tmA, tmB, p, grid, st);
+  return tc_gemm_launch<BN, false, false>(tmA, tmB, p, grid, st);
+}
+
+// Tile width: 128 columns unless that leaves most SMs idle (few tiles, no split-K), then 64 / 32.
+inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
+  const bool b_mn = g.b_k != 1;
+  const int num_kb = cdiv(g.K, kTcBK);
+  const int splits = g.splits < 1 ? 1 : (g.splits < num_kb ? g.splits : num_kb);
+  const long long tm = cdiv(g.M, kTcBM);
+  const int half = tc_num_sms() / 2;
+  int bn = 128;
+  if (tm * cdiv(g.N, 128) * splits < half && g.N > 64) bn = 64;
+  if (bn == 64 && tm * cdiv(g.N, 64) * splits < half && g.N > 32 && !b_mn) bn = 32;
+  if (bn == 128) return tc_gemm_bn<128>(g, st);
+  if (bn == 64) return tc_gemm_bn<64>(g, st);
+  return tc_gemm_bn<32>(g, st);
 }
 
 }  // namespace dic

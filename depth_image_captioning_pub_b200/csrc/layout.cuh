@@ -74,7 +74,7 @@ constexpr int kGateSplitsMax = 16;
 // Training workspace (forward state saved for backward + backward scratch).
 struct TrainLayout {
   size_t Fsum, meanF, att1, XH, HP, Z, acts, c_all, gate_part, Hdrop;
-  size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16;
+  size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16, dal_part, h0;
   size_t bytes;
   size_t XW, GW;
   int es;
@@ -108,6 +108,8 @@ struct TrainLayout {
     dmeanF = c.take(sizeof(float) * B * d.D);
     tmpvec = c.take(sizeof(float) * (GW + 16));
     dlogits16 = c.take(dtype == DIC_BF16 ? TB * d.V * 2 : 16);   // bf16 copy of d_logits (GEMM operand)
+    dal_part = c.take(sizeof(float) * (size_t)((d.D + 255) / 256) * B * d.L);   // per-chunk dalpha partials
+    h0 = c.take(sizeof(float) * B * d.H);
     bytes = c.off;
   }
 };
@@ -115,7 +117,7 @@ struct TrainLayout {
 // Decode workspace: R = B*beam rows.
 struct DecodeLayout {
   size_t Fsum, meanF, att1, XH, HP, c, c_tmp, h_tmp, h0, c0, gate_part, logits, lse;
-  size_t scores, scores2, fin, fin2, back, tok, step_scores;
+  size_t scores, scores2, fin, fin2, back, tok, step_scores, alpha;
   size_t bytes;
   size_t XW;
   int es;
@@ -144,6 +146,7 @@ struct DecodeLayout {
     back = c_.take(sizeof(int32_t) * R * max_len);
     tok = c_.take(sizeof(int32_t) * R * max_len);
     step_scores = c_.take(sizeof(float) * R * max_len);
+    alpha = c_.take(sizeof(float) * R * d.L);
     bytes = c_.off;
   }
 };

@@ -29,12 +29,22 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
   if (idx >= p.rows * p.H) return;
   const int r = idx / p.H, j = idx - r * p.H;
   const int H = p.H;
+  // reduce the split-K partial tiles in a fixed order (deterministic); all loads are issued
+  // before the adds so the up-to-64 L2 reads of a thread overlap
   float g4[4];
+  constexpr int kMaxSplits = 16;
+  float part[4][kMaxSplits];
+#pragma unroll
+  for (int sp = 0; sp < kMaxSplits; ++sp) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      part[q][sp] = sp < p.splits ? p.gate_part[(size_t)sp * p.part_stride + (size_t)r * 4 * H + q * H + j] : 0.f;
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float s = p.bias_g[q * H + j];
-    for (int sp = 0; sp < p.splits; ++sp)
-      s += p.gate_part[(size_t)sp * p.part_stride + (size_t)r * 4 * H + q * H + j];
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplits; ++sp) s += part[q][sp];
     g4[q] = s;
   }
   const float ig = sigmoidf_acc(g4[0]);

@@ -155,10 +155,29 @@ __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ s
   }
 }
 
+// contiguous fp32 -> bf16 cast, 8 elements per thread (16-byte stores)
+__global__ void __launch_bounds__(256) cast_bf16_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
+                                                            size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+    float v[8];
+    load8_stream<float>(src + i * 8, v);
+    store8<bf16>(dst + i * 8, v);
+  }
+}
+
 inline int launch_copy2d(const float* src, long long src_ld, void* dst, long long dst_ld, int dst_bf16,
                          int R, int C, cudaStream_t st) {
   const size_t n = (size_t)R * C;
   if (n == 0) return 0;
+  if (dst_bf16 && src_ld == C && dst_ld == C && n % 8 == 0 && n >= (1u << 16) &&
+      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    size_t n8 = n / 8;
+    int blocks = (int)((n8 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cast_bf16_vec_kernel<<<blocks, 256, 0, st>>>(src, reinterpret_cast<bf16*>(dst), n8);
+    DIC_LAUNCH_CHECK();
+    return 0;
+  }
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   copy2d_kernel<<<blocks, 256, 0, st>>>(src, src_ld, dst, dst_ld, dst_bf16, R, C);
@@ -169,6 +188,85 @@ inline int launch_copy2d(const float* src, long long src_ld, void* dst, long lon
 __global__ void __launch_bounds__(256) add_vec_kernel(const float* a, const float* b, float* dst, int n) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < n) dst[i] = a[i] + b[i];
+}
+
+// ---- dL/dF accumulation -------------------------------------------------------------------------
+//   dF[b,l,d] (+)= sum_t alpha_t[b,l] * dz_t[b,d] + dmeanF[b,d] / L
+// the context path (attention.py:93) and the mean path (depth_models.py:166) of the annotation
+// gradient; the encoder_att path (datt1 . W_enc) is written first by the tensor-core GEMM, this
+// kernel adds the rest in place.  Memory bound (one read + one write of dF).
+// Grid (D/512, B); 8 warps x 64 columns; each thread owns 2 columns and keeps its dz_t values for a
+// tile of up to 32 steps in registers; alpha^T sits in shared memory as [L][32].
+constexpr int kDfeatTT = 32;
+template <typename ST>
+__global__ void __launch_bounds__(256) dfeat_accumulate_kernel(float* __restrict__ dF, const float* __restrict__ alphas,
+                                                               const ST* __restrict__ DZ,
+                                                               const float* __restrict__ dmeanF, int B, int L, int D,
+                                                               int T, int accumulate) {
+  extern __shared__ __align__(16) float al_s[];   // [L][kDfeatTT]
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * 512 + threadIdx.x * 2;
+  const bool active = d < D;
+  float* out = dF + (size_t)b * L * D + d;
+  const float inv_l = 1.f / (float)L;
+  for (int t0 = 0; t0 < T; t0 += kDfeatTT) {
+    const int tn = min(kDfeatTT, T - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * kDfeatTT; i += 256) {
+      const int l = i / kDfeatTT, t = i - l * kDfeatTT;
+      al_s[i] = t < tn ? alphas[((size_t)b * T + t0 + t) * L + l] : 0.f;
+    }
+    float dz0[kDfeatTT], dz1[kDfeatTT];
+#pragma unroll
+    for (int t = 0; t < kDfeatTT; ++t) {
+      dz0[t] = 0.f; dz1[t] = 0.f;
+      if (active && t < tn) {
+        const ST* src = DZ + ((size_t)(t0 + t) * B + b) * D + d;
+        dz0[t] = to_f<ST>(src[0]);
+        dz1[t] = to_f<ST>(src[1]);
+      }
+    }
+    float m0 = 0.f, m1 = 0.f;
+    if (active && t0 == 0 && dmeanF) {
+      m0 = dmeanF[(size_t)b * D + d] * inv_l;
+      m1 = dmeanF[(size_t)b * D + d + 1] * inv_l;
+    }
+    __syncthreads();
+    if (active) {
+      const bool rmw = accumulate || t0 > 0;
+#pragma unroll 2
+      for (int l = 0; l < L; ++l) {
+        float2 acc = rmw ? *reinterpret_cast<const float2*>(out + (size_t)l * D) : make_float2(0.f, 0.f);
+        acc.x += m0; acc.y += m1;
+        const float4* ar = reinterpret_cast<const float4*>(al_s + l * kDfeatTT);
+#pragma unroll
+        for (int t4 = 0; t4 < kDfeatTT / 4; ++t4) {
+          const float4 a = ar[t4];
+          acc.x = fmaf(a.x, dz0[4 * t4], acc.x);     acc.y = fmaf(a.x, dz1[4 * t4], acc.y);
+          acc.x = fmaf(a.y, dz0[4 * t4 + 1], acc.x); acc.y = fmaf(a.y, dz1[4 * t4 + 1], acc.y);
+          acc.x = fmaf(a.z, dz0[4 * t4 + 2], acc.x); acc.y = fmaf(a.z, dz1[4 * t4 + 2], acc.y);
+          acc.x = fmaf(a.w, dz0[4 * t4 + 3], acc.x); acc.y = fmaf(a.w, dz1[4 * t4 + 3], acc.y);
+        }
+        *reinterpret_cast<float2*>(out + (size_t)l * D) = acc;
+      }
+    }
+  }
+}
+
+template <typename ST>
+inline int launch_dfeat_accumulate(float* dF, const float* alphas, const ST* DZ, const float* dmeanF, int B, int L,
+                                   int D, int T, int accumulate, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIC_CUDA(cudaFuncSetAttribute(dfeat_accumulate_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  ProfScope prof(P_DFEAT, st, 2.0 * (double)B * L * D * sizeof(float));
+  dim3 grid(cdiv(D, 512), B);
+  dfeat_accumulate_kernel<ST><<<grid, 256, sizeof(float) * L * kDfeatTT, st>>>(dF, alphas, DZ, dmeanF, B, L, D, T,
+                                                                            accumulate);
+  DIC_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace dic

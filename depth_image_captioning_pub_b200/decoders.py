@@ -53,7 +53,9 @@ class _DecoderBase(nn.Module):
         self.linear = nn.Linear(dim_decoder, vocab_size)
         self._reset_parameters()
         self.precision = DEFAULT_PRECISION
-        self._dims = (dim_attention, dim_embedding, dim_encoder, dim_decoder, vocab_size)
+        # decode calls re-pack the weights every time unless the caller declares them frozen
+        self.cache_packed_weights = False
+        self._dims =(dim_attention, dim_embedding, dim_encoder, dim_decoder, vocab_size)
         self._engines: Dict = {}
 
     def _reset_parameters(self):
@@ -128,7 +130,7 @@ class _DecoderBase(nn.Module):
     def _greedy(self, attn_mode, features, depth_features, word_to_id, max_length, want_alphas):
         features, depth_features = self._check_feats(features, depth_features)
         eng = self._engine(features.shape[1], features.device)
-        eng.ensure_packed(self._param_list())
+        eng.ensure_packed(self._param_list(), allow_cached=self.cache_packed_weights)
         u = None
         if attn_mode == _lib.ATTN_GUMBEL_MAX:
             u = self._draw_u(max_length * features.shape[0], features.shape[1], features.device)
@@ -140,7 +142,7 @@ class _DecoderBase(nn.Module):
     def _beam(self, features, depth_features, word_to_id, beam, max_length, trace=False):
         features, depth_features = self._check_feats(features, depth_features)
         eng = self._engine(features.shape[1], features.device)
-        eng.ensure_packed(self._param_list())
+        eng.ensure_packed(self._param_list(), allow_cached=self.cache_packed_weights)
         return eng.beam(features, depth_features, word_to_id['<start>'], word_to_id['<end>'], beam, max_length,
                         trace=trace)
 

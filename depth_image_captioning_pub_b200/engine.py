@@ -56,11 +56,18 @@ class Engine:
         self._ws: Dict[Tuple, torch.Tensor] = {}
 
     # ---- weights -------------------------------------------------------------------------
-    def ensure_packed(self, params: Sequence[torch.Tensor]) -> None:
-        """(Re)build the compute-layout weight pack when any parameter changed."""
+    def ensure_packed(self, params: Sequence[torch.Tensor], allow_cached: bool = False) -> None:
+        """(Re)build the compute-layout weight pack.
+
+        The pack is rebuilt on EVERY call by default: tensor version counters are not a safe
+        change detector (fused optimizers such as AdamW(fused=True) update parameters without
+        bumping them), and a stale pack would silently decode/train with old weights.  Callers
+        that know the weights are frozen (inference loops) may pass allow_cached=True.
+        """
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if key == self._pack_key:
+        if allow_cached and key == self._pack_key:
             return
+        self._pack_serial = getattr(self, "_pack_serial", 0) + 1
         with torch.cuda.device(self.device):
             ps = _params_struct([p.detach().contiguous() for p in params])
             _lib.check(self.lib.dic_pack_weights(C.byref(self.dims), self.dtype, C.byref(ps),
