@@ -78,34 +78,68 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
   const float b_full = p.b_full[0];
   const int half = lane >> 4, hl = lane & 15;
   constexpr int RPW = 2 * (kAlphaThreads / 32);      // rows per CTA pass (16)
-  for (int lb = 0; lb < L; lb += RPW) {
-    const int l = lb + warp * 2 + half;
-    float acc[KB];
+  if (A == 128) {
+    // Reference shape: one 16-byte load covers a lane's 8 columns.  The whole att1 slab of the image
+    // is put in flight first (kAlphaIters independent loads per thread), then consumed: the kernel is
+    // a pure latency chain otherwise (one 50 KB slab per CTA).
+    constexpr int IT = 13;                            // 13 * 16 rows >= 196
+    for (int lb0 = 0; lb0 < L; lb0 += IT * RPW) {
+      Raw8<ST> raw[IT];
 #pragma unroll
-    for (int j = 0; j < KB; ++j) acc[j] = 0.f;
-    if (l < L) {
-      for (int a = hl * 8; a < A; a += 128) {
+      for (int it = 0; it < IT; ++it) {
+        const int l = lb0 + it * RPW + warp * 2 + half;
+        if (l < L) raw[it].load_stream(att1 + (size_t)l * A + hl * 8);
+        else raw[it].zero();
+      }
+      float w8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w8[q] = w_s[hl * 8 + q];
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int l = lb0 + it * RPW + warp * 2 + half;
         float v[8];
-        if (a + 8 <= A) {
-          load8<ST>(att1 + (size_t)l * A + a, v);
-        } else {   // A % 8 == 4 tail
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = (a + q < A) ? to_f<ST>(att1[(size_t)l * A + a + q]) : 0.f;
-        }
+        raw[it].unpack(v);
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
+          float s = 0.f;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (a + q < A) acc[j] = fmaf(fmaxf(v[q] + att2_s[j * A + a + q], 0.f), w_s[a + q], acc[j]);
+          for (int q = 0; q < 8; ++q) s = fmaf(fmaxf(v[q] + att2_s[j * A + hl * 8 + q], 0.f), w8[q], s);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (hl == 0 && l < L) e_s[j * Lp + l] = s + b_full;
         }
       }
     }
+  } else {
+    for (int lb = 0; lb < L; lb += RPW) {
+      const int l = lb + warp * 2 + half;
+      float acc[KB];
 #pragma unroll
-    for (int j = 0; j < KB; ++j) {
-      float s = acc[j];
+      for (int j = 0; j < KB; ++j) acc[j] = 0.f;
+      if (l < L) {
+        for (int a = hl * 8; a < A; a += 128) {
+          float v[8];
+          if (a + 8 <= A) {
+            load8<ST>(att1 + (size_t)l * A + a, v);
+          } else {   // A % 8 == 4 tail
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (hl == 0 && l < L) e_s[j * Lp + l] = s + b_full;
+            for (int q = 0; q < 8; ++q) v[q] = (a + q < A) ? to_f<ST>(att1[(size_t)l * A + a + q]) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (a + q < A) acc[j] = fmaf(fmaxf(v[q] + att2_s[j * A + a + q], 0.f), w_s[a + q], acc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KB; ++j) {
+        float s = acc[j];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (hl == 0 && l < L) e_s[j * Lp + l] = s + b_full;
+      }
     }
   }
   __syncthreads();
@@ -454,10 +488,11 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
 }
 
 constexpr int kBwdSmallThreads = 256;
+constexpr int kBwdRowGroups = 16;
 
 inline size_t attn_bwd_small_smem_bytes(int L, int A) {
-  // de[L] | al[L] | w[A] | att2[A] | red[2][2][A] | scratch[64]
-  return sizeof(float) * (2 * (size_t)L + 2 * (size_t)A + 4 * (size_t)A + 64);
+  // de[L] | al[L] | w[A] | att2[A] | red[2][16][A] | scratch[64]
+  return sizeof(float) * (2 * (size_t)L + 2 * (size_t)A + 2 * kBwdRowGroups * (size_t)A + 64);
 }
 
 template <typename ST>
@@ -468,8 +503,8 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
   float* al_s = de_s + L;
   float* w_s = al_s + L;
   float* att2_s = w_s + A;
-  float* red_s = att2_s + A;       // [2][2][A]
-  float* scratch = red_s + 4 * A;  // 64
+  float* red_s = att2_s + A;                          // [2][kBwdRowGroups][A]
+  float* scratch = red_s + 2 * kBwdRowGroups * A;     // 64
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const float* hp = p.hp + (size_t)b * (A + D);
@@ -500,31 +535,75 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
   const float dbf = block_sum(desum, scratch);   // its barriers also publish de_s
   if (tid == 0) p.dbfull_part[b] = dbf;
 
-  // relu-mask pass over att1: thread (column a, row group)
+  // relu-mask pass over att1.  red_s holds [2][kBwdRowGroups][A] partial sums.
   const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)b * L * A;
-  const int rg = tid >> 7, a0 = tid & 127;   // 2 row groups x 128 columns
-  for (int ab = 0; ab < A; ab += 128) {
-    const int a = ab + a0;
-    if (a < A) {
-      const float a2 = att2_s[a];
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-      for (int l = rg; l < L; l += 2) {
-        const float pre = to_f<ST>(att1[(size_t)l * A + a]) + a2;
-        if (pre > 0.f) {
+  if (A == 128) {
+    // reference shape: 16 column groups (8 columns, one 16-byte load) x 16 row groups; the image's
+    // whole att1 slab is put in flight before it is consumed (latency-bound kernel otherwise)
+    constexpr int IT = 13;
+    const int cg = tid & 15, rgp = tid >> 4;
+    float a2[8], s1[8], s2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { a2[q] = att2_s[cg * 8 + q]; s1[q] = 0.f; s2[q] = 0.f; }
+    for (int l0 = 0; l0 < L; l0 += IT * kBwdRowGroups) {
+      Raw8<ST> raw[IT];
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int l = l0 + it * kBwdRowGroups + rgp;
+        if (l < L) raw[it].load_stream(att1 + (size_t)l * A + cg * 8);
+        else raw[it].zero();
+      }
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int l = l0 + it * kBwdRowGroups + rgp;
+        if (l < L) {
+          float v[8];
+          raw[it].unpack(v);
           const float de = de_s[l];
-          s1 += de;
-          s2 = fmaf(de, pre, s2);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float pre = v[q] + a2[q];
+            if (pre > 0.f) { s1[q] += de; s2[q] = fmaf(de, pre, s2[q]); }
+          }
         }
       }
-      red_s[(0 * 2 + rg) * A + a] = s1;
-      red_s[(1 * 2 + rg) * A + a] = s2;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      red_s[(0 * kBwdRowGroups + rgp) * A + cg * 8 + q] = s1[q];
+      red_s[(1 * kBwdRowGroups + rgp) * A + cg * 8 + q] = s2[q];
+    }
+  } else {
+    for (int i = tid; i < 2 * kBwdRowGroups * A; i += kBwdSmallThreads) red_s[i] = 0.f;
+    __syncthreads();
+    const int rg = tid >> 7, a0 = tid & 127;   // 2 row groups x 128 columns
+    for (int ab = 0; ab < A; ab += 128) {
+      const int a = ab + a0;
+      if (a < A) {
+        const float a2 = att2_s[a];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+        for (int l = rg; l < L; l += 2) {
+          const float pre = to_f<ST>(att1[(size_t)l * A + a]) + a2;
+          if (pre > 0.f) {
+            const float de = de_s[l];
+            s1 += de;
+            s2 = fmaf(de, pre, s2);
+          }
+        }
+        red_s[(0 * kBwdRowGroups + rg) * A + a] = s1;
+        red_s[(1 * kBwdRowGroups + rg) * A + a] = s2;
+      }
     }
   }
   __syncthreads();
   for (int a = tid; a < A; a += kBwdSmallThreads) {
-    const float s1 = red_s[0 * A + a] + red_s[1 * A + a];
-    const float s2 = red_s[2 * A + a] + red_s[3 * A + a];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < kBwdRowGroups; ++g) {
+      s1 += red_s[(0 * kBwdRowGroups + g) * A + a];
+      s2 += red_s[(1 * kBwdRowGroups + g) * A + a];
+    }
     G[p.gcol_att2 + a] = from_f<ST>(w_s[a] * s1);
     p.dwfull_part[(size_t)b * A + a] = s2;
   }

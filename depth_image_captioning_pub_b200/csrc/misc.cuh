@@ -85,8 +85,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ sr
   const int c = blockIdx.x * 32 + cx;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
   float s = 0.f;
-  if (c < C)
-    for (int r = r0 + ry; r < r1; r += 8) s += ld_as_float(src, (size_t)r * ld + c, src_bf16);
+  if (c < C) {
+    int r = r0 + ry;
+    for (; r + 56 < r1; r += 64) {      // 8 independent loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ld_as_float(src, (size_t)(r + 8 * i) * ld + c, src_bf16);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[i];
+    }
+    for (; r < r1; r += 8) s += ld_as_float(src, (size_t)r * ld + c, src_bf16);
+  }
   red[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && c < C) {
@@ -234,20 +243,30 @@ __global__ void __launch_bounds__(256) dfeat_accumulate_kernel(float* __restrict
     __syncthreads();
     if (active) {
       const bool rmw = accumulate || t0 > 0;
-#pragma unroll 2
-      for (int l = 0; l < L; ++l) {
-        float2 acc = rmw ? *reinterpret_cast<const float2*>(out + (size_t)l * D) : make_float2(0.f, 0.f);
-        acc.x += m0; acc.y += m1;
-        const float4* ar = reinterpret_cast<const float4*>(al_s + l * kDfeatTT);
+      constexpr int RB = 7;   // rows in flight per thread (the kernel is a read-modify-write stream)
+      for (int l0 = 0; l0 < L; l0 += RB) {
+        float2 acc[RB];
 #pragma unroll
-        for (int t4 = 0; t4 < kDfeatTT / 4; ++t4) {
-          const float4 a = ar[t4];
-          acc.x = fmaf(a.x, dz0[4 * t4], acc.x);     acc.y = fmaf(a.x, dz1[4 * t4], acc.y);
-          acc.x = fmaf(a.y, dz0[4 * t4 + 1], acc.x); acc.y = fmaf(a.y, dz1[4 * t4 + 1], acc.y);
-          acc.x = fmaf(a.z, dz0[4 * t4 + 2], acc.x); acc.y = fmaf(a.z, dz1[4 * t4 + 2], acc.y);
-          acc.x = fmaf(a.w, dz0[4 * t4 + 3], acc.x); acc.y = fmaf(a.w, dz1[4 * t4 + 3], acc.y);
+        for (int r = 0; r < RB; ++r) {
+          acc[r] = make_float2(0.f, 0.f);
+          if (rmw && l0 + r < L) acc[r] = *reinterpret_cast<const float2*>(out + (size_t)(l0 + r) * D);
         }
-        *reinterpret_cast<float2*>(out + (size_t)l * D) = acc;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (l0 + r >= L) continue;
+          float2 a2 = acc[r];
+          a2.x += m0; a2.y += m1;
+          const float4* ar = reinterpret_cast<const float4*>(al_s + (l0 + r) * kDfeatTT);
+#pragma unroll
+          for (int t4 = 0; t4 < kDfeatTT / 4; ++t4) {
+            const float4 a = ar[t4];
+            a2.x = fmaf(a.x, dz0[4 * t4], a2.x);     a2.y = fmaf(a.x, dz1[4 * t4], a2.y);
+            a2.x = fmaf(a.y, dz0[4 * t4 + 1], a2.x); a2.y = fmaf(a.y, dz1[4 * t4 + 1], a2.y);
+            a2.x = fmaf(a.z, dz0[4 * t4 + 2], a2.x); a2.y = fmaf(a.z, dz1[4 * t4 + 2], a2.y);
+            a2.x = fmaf(a.w, dz0[4 * t4 + 3], a2.x); a2.y = fmaf(a.w, dz1[4 * t4 + 3], a2.y);
+          }
+          *reinterpret_cast<float2*>(out + (size_t)(l0 + r) * D) = a2;
+        }
       }
     }
   }
