@@ -141,7 +141,8 @@ struct TcArgs {
 
 template <int BN>
 constexpr size_t tc_smem_bytes() {
-  return 1024 /*align slack*/ + (size_t)kTcStages * (kTcBM * kTcBK * 2 + BN * kTcBK * 2) + 256;
+  return 1024 /*align slack*/ + (size_t)kTcStages * (kTcBM * kTcBK * 2 + BN * kTcBK * 2) + 256 /*barriers*/ +
+         (size_t)kTcEpiWarps * 32 * 33 * sizeof(float) /*epilogue staging*/;
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -163,6 +164,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bar_base + 8u * (2 * kTcStages + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // per-epilogue-warp staging tiles [32][33] fp32 (store transpose), after the barrier block
+  float* stage_base = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + kTcBK - 1) / kTcBK;
@@ -295,57 +298,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-      const int m = m0 + q * 32 + lane;
-      if (grp < GROUPS && m < p.M) {
+      // Stores go through a per-warp shared-memory transpose: after tcgen05.ld a thread owns one
+      // ROW of the tile (32 consecutive columns), which would make every store instruction touch 32
+      // different 128-byte lines.  Staged through smem, each instruction writes one row segment of
+      // 32 consecutive columns (one full line for fp32) -- 8x fewer memory requests.
+      if (grp < GROUPS) {
+        float* stg = stage_base + ew * (32 * 33);
         char* Cb = reinterpret_cast<char*>(p.C);
-        size_t cbase = (size_t)m * p.ldc;
-        if (p.splits > 1 && p.split_mode == 1) cbase += (size_t)split * p.split_stride;
+        const int mrow0 = m0 + q * 32;
+        size_t coff = 0;
+        if (p.splits > 1 && p.split_mode == 1) coff = (size_t)split * p.split_stride;
         const bool atomic = p.splits > 1 && p.split_mode == 0;
         const bool add_bias = p.bias != nullptr && split == 0;
+        const int rows_valid = min(32, p.M - mrow0);
 #pragma unroll
         for (int c = 0; c < COLS / 32; ++c) {
           const int nb = n0 + grp * COLS + c * 32;
-          if (nb >= p.N) continue;
-          float v[32];
+          if (nb >= p.N || rows_valid <= 0) continue;      // warp-uniform
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[c][j]) * p.alpha;
             const int n = nb + j;
             if (add_bias && n < p.N) x += p.bias[n];
             if (n >= p.sig_lo && n < p.sig_hi) x = sigmoidf_acc(x);
-            v[j] = x;
+            stg[lane * 33 + j] = x;
           }
-          if (atomic) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) atomicAdd(reinterpret_cast<float*>(Cb) + cbase + nb + j, v[j]);
-          } else if (p.c_bf16) {
-            bf16* dst = reinterpret_cast<bf16*>(Cb) + cbase + nb;
-            if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) t8[e] = v[j + e];
-                store8<bf16>(dst + j, t8);
-              }
+          __syncwarp();
+          const int n = nb + lane;
+          if (n < p.N) {
+            if (atomic) {
+              float* dst = reinterpret_cast<float*>(Cb) + coff + (size_t)mrow0 * p.ldc + n;
+              for (int rr = 0; rr < rows_valid; ++rr) atomicAdd(dst + (size_t)rr * p.ldc, stg[rr * 33 + lane]);
+            } else if (p.c_bf16) {
+              bf16* dst = reinterpret_cast<bf16*>(Cb) + coff + (size_t)mrow0 * p.ldc + n;
+              for (int rr = 0; rr < rows_valid; ++rr) dst[(size_t)rr * p.ldc] = __float2bfloat16_rn(stg[rr * 33 + lane]);
             } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else {
-            float* dst = reinterpret_cast<float*>(Cb) + cbase + nb;
-            if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) dst[j] = v[j];
+              float* dst = reinterpret_cast<float*>(Cb) + coff + (size_t)mrow0 * p.ldc + n;
+#pragma unroll 8
+              for (int rr = 0; rr < rows_valid; ++rr) dst[(size_t)rr * p.ldc] = stg[rr * 33 + lane];
             }
           }
+          __syncwarp();
         }
       }
     }

@@ -12,6 +12,7 @@ from depth_image_captioning_pub_b200 import _lib  # noqa: E402
 dev = torch.device("cuda:0")
 lib = _lib.load()
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+only = sys.argv[2] if len(sys.argv) > 2 else None
 
 # name, M, N, K, A layout, B layout, splits, ideal bytes (for GB/s)
 SHAPES = [
@@ -32,6 +33,8 @@ SHAPES = [
 
 print(f"{'gemm':34s} {'M':>6s} {'N':>6s} {'K':>6s}   tc us   fma us   tc TFLOP/s")
 for name, M, N, K, la, lb, splits in SHAPES:
+    if only and not name.startswith(only):
+        continue
     A = torch.randn(M, K, device=dev).to(torch.bfloat16)
     B = torch.randn(N, K, device=dev).to(torch.bfloat16)
     if la == "k":
