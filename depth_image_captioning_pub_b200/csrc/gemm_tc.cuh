@@ -142,7 +142,7 @@ struct TcArgs {
 template <int BN>
 constexpr size_t tc_smem_bytes() {
   return 1024 /*align slack*/ + (size_t)kTcStages * (kTcBM * kTcBK * 2 + BN * kTcBK * 2) + 256 /*barriers*/ +
-         (size_t)kTcEpiWarps * 32 * 33 * sizeof(float) /*epilogue staging*/;
+         (size_t)kTcEpiWarps * 32 * 36 * sizeof(float) /*epilogue staging*/;
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -164,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bar_base + 8u * (2 * kTcStages + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  // per-epilogue-warp staging tiles [32][33] fp32 (store transpose), after the barrier block
+  // per-epilogue-warp staging tiles [32][36] fp32 (store transpose), after the barrier block
   float* stage_base = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -298,45 +298,83 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-      // Stores go through a per-warp shared-memory transpose: after tcgen05.ld a thread owns one
-      // ROW of the tile (32 consecutive columns), which would make every store instruction touch 32
-      // different 128-byte lines.  Staged through smem, each instruction writes one row segment of
-      // 32 consecutive columns (one full line for fp32) -- 8x fewer memory requests.
+      // Stores go through a per-warp shared-memory transpose: after tcgen05.ld a thread owns one ROW
+      // of the tile (32 consecutive columns), which would make every store instruction touch 32
+      // different 128-byte lines.  Staged through smem ([32][36] fp32, 16-byte accesses both ways,
+      // conflict free), one warp instruction writes 4 full 128-byte row segments.  The epilogue was
+      // instruction bound before this (ncu: 15k warp instructions per 64 KB tile), so everything
+      // here is 128-bit wide and the bias / activation math is skipped when not requested.
       if (grp < GROUPS) {
-        float* stg = stage_base + ew * (32 * 33);
-        char* Cb = reinterpret_cast<char*>(p.C);
+        float* stg = stage_base + ew * (32 * 36);
         const int mrow0 = m0 + q * 32;
         size_t coff = 0;
         if (p.splits > 1 && p.split_mode == 1) coff = (size_t)split * p.split_stride;
         const bool atomic = p.splits > 1 && p.split_mode == 0;
         const bool add_bias = p.bias != nullptr && split == 0;
+        const bool plain = !add_bias && p.sig_hi <= p.sig_lo && p.alpha == 1.f;
         const int rows_valid = min(32, p.M - mrow0);
+        const int esz = p.c_bf16 ? 2 : 4;
+        const bool vec_ok = ((p.ldc * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) + coff * esz) % 16 == 0);
+        const int rrow = lane >> 3, col4 = (lane & 7) * 4;
 #pragma unroll
         for (int c = 0; c < COLS / 32; ++c) {
           const int nb = n0 + grp * COLS + c * 32;
           if (nb >= p.N || rows_valid <= 0) continue;      // warp-uniform
+          if (plain) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[c][j]) * p.alpha;
-            const int n = nb + j;
-            if (add_bias && n < p.N) x += p.bias[n];
-            if (n >= p.sig_lo && n < p.sig_hi) x = sigmoidf_acc(x);
-            stg[lane * 33 + j] = x;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(stg + lane * 36 + j) = make_uint4(r[c][j], r[c][j + 1], r[c][j + 2], r[c][j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float x[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int n = nb + j + e;
+                float t = __uint_as_float(r[c][j + e]) * p.alpha;
+                if (add_bias && n < p.N) t += p.bias[n];
+                if (n >= p.sig_lo && n < p.sig_hi) t = sigmoidf_acc(t);
+                x[e] = t;
+              }
+              *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(x[0], x[1], x[2], x[3]);
+            }
           }
           __syncwarp();
-          const int n = nb + lane;
-          if (n < p.N) {
-            if (atomic) {
-              float* dst = reinterpret_cast<float*>(Cb) + coff + (size_t)mrow0 * p.ldc + n;
-              for (int rr = 0; rr < rows_valid; ++rr) atomicAdd(dst + (size_t)rr * p.ldc, stg[rr * 33 + lane]);
-            } else if (p.c_bf16) {
-              bf16* dst = reinterpret_cast<bf16*>(Cb) + coff + (size_t)mrow0 * p.ldc + n;
-              for (int rr = 0; rr < rows_valid; ++rr) dst[(size_t)rr * p.ldc] = __float2bfloat16_rn(stg[rr * 33 + lane]);
-            } else {
-              float* dst = reinterpret_cast<float*>(Cb) + coff + (size_t)mrow0 * p.ldc + n;
-#pragma unroll 8
-              for (int rr = 0; rr < rows_valid; ++rr) dst[(size_t)rr * p.ldc] = stg[rr * 33 + lane];
+          const int n = nb + col4;
+          char* crow = reinterpret_cast<char*>(p.C) + (coff + (size_t)(mrow0 + rrow) * p.ldc + n) * esz;
+          const size_t rstep = (size_t)4 * p.ldc * esz;
+          const bool full = vec_ok && (n + 3 < p.N);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rrow;
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + col4);
+            if (rr < rows_valid && n < p.N) {
+              if (full) {
+                if (atomic) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow), "f"(v.x), "f"(v.y),
+                               "f"(v.z), "f"(v.w) : "memory");
+                } else if (p.c_bf16) {
+                  uint2 pk;
+                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+                  h2[0] = __floats2bfloat162_rn(v.x, v.y);
+                  h2[1] = __floats2bfloat162_rn(v.z, v.w);
+                  *reinterpret_cast<uint2*>(crow) = pk;
+                } else {
+                  *reinterpret_cast<float4*>(crow) = v;
+                }
+              } else {
+                const float ve[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (n + e < p.N) {
+                    if (atomic) atomicAdd(reinterpret_cast<float*>(crow) + e, ve[e]);
+                    else if (p.c_bf16) reinterpret_cast<bf16*>(crow)[e] = __float2bfloat16_rn(ve[e]);
+                    else reinterpret_cast<float*>(crow)[e] = ve[e];
+                  }
+                }
+              }
             }
+            crow += rstep;
           }
           __syncwarp();
         }
