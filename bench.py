@@ -203,27 +203,16 @@ def run_b200(args):
     F_rgb = F_rgb_h.to(dev)
     F_dep = F_dep_h.to(dev).requires_grad_(True)     # the depth CNN is trained: dL/dF_depth is part of the step
     caps = caps_h.to(dev)
-    flat = None
-    if world > 1:
-        n = sum(p.numel() for p in params)
-        flat = torch.empty(n, dtype=torch.float32, device=dev)
+    from depth_image_captioning_pub_b200.distributed import FlatGradAllReduce
+    allreduce = FlatGradAllReduce(params) if world > 1 else None
 
     def train_step(fr, fd, cp):
         out, alphas = m(fr, fd, cp, lengths)
         loss = torch.nn.functional.cross_entropy(out.data, targets, ignore_index=V - 1)
         loss = loss + LAM * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
         loss.backward()
-        if world > 1:   # data parallel: one flat fp32 NCCL all-reduce over NVLink
-            o = 0
-            for p in params:
-                flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
-                o += p.numel()
-            dist.all_reduce(flat)
-            flat.mul_(1.0 / world)
-            o = 0
-            for p in params:
-                p.grad.copy_(flat[o:o + p.numel()].view_as(p))
-                o += p.numel()
+        if allreduce is not None:   # data parallel: one flat fp32 NCCL all-reduce over NVLink
+            allreduce(average=True)
         opt.step()
         opt.zero_grad(set_to_none=True)
         fd.grad = None

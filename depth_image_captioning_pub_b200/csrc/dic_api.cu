@@ -235,7 +235,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
                                  const int64_t* captions, int cap_stride, const StepSizes& sizes,
                                  int total, int T, int B, const float* d_logits, const float* d_alphas,
                                  const float* alphas, float temp, const float* dropout_mask,
-                                 const dic_params& gr, float* d_feats, const void* f_rgb_alias, char* ws,
+                                 const dic_params& gr, void* d_feats, int dfeat_bf16, const void* f_rgb_alias, char* ws,
                                  cudaStream_t st) {
   const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
   const int is_bf16 = sizeof(ST) == 2;
@@ -414,11 +414,14 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   }
 
   // dL/dF = datt1 . W_enc + sum_t alpha_t (x) dz_t + dmeanF / L
+  // (written in the annotations' dtype: fp32 in place, bf16 through the fp32 accumulation buffer dF32)
   if (d_feats) {
-    GemmArgs g = gemm_args_nt(datt1, is_bf16, A, pk.Wenc(), is_bf16, 0, d_feats, 0, D, B * L, D, A, nullptr);
+    float* acc = dfeat_bf16 ? reinterpret_cast<float*>(ws + lay.dF32) : reinterpret_cast<float*>(d_feats);
+    GemmArgs g = gemm_args_nt(datt1, is_bf16, A, pk.Wenc(), is_bf16, 0, acc, 0, D, B * L, D, A, nullptr);
     g.b_n = 1; g.b_k = D;
     DIC_TRY(gemm(g, st));
-    DIC_TRY(launch_dfeat_accumulate<ST>(d_feats, alphas, DZ, dmeanF, B, L, D, T, 1, st));
+    DIC_TRY(launch_dfeat_accumulate<ST>(acc, alphas, DZ, dmeanF, B, L, D, T, 1,
+                                        dfeat_bf16 ? reinterpret_cast<bf16*>(d_feats) : nullptr, st));
   }
   return 0;
 }
@@ -652,7 +655,7 @@ int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const v
                          const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
                          const int32_t* host_batch_sizes, int T, int B, const float* d_logits,
                          const float* d_alphas, const float* alphas, float temp, const float* dropout_mask,
-                         const dic_params* grads, float* d_feats, void* workspace, size_t workspace_bytes,
+                         const dic_params* grads, void* d_feats, void* workspace, size_t workspace_bytes,
                          void* stream) {
   DIC_TRY(check_dims(dims, dtype));
   // same aliasing rule as prologue(): no fused copy was made when there is no depth tensor and
@@ -670,10 +673,12 @@ int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const v
   char* ws = reinterpret_cast<char*>(workspace);
   if (dtype == DIC_BF16)
     return decoder_backward_impl<bf16>(*dims, attn_mode, pack, captions, cap_stride, sizes, total, T, B,
-                                       d_logits, d_alphas, alphas, temp, dropout_mask, *grads, d_feats, f_alias,
+                                       d_logits, d_alphas, alphas, temp, dropout_mask, *grads, d_feats,
+                                       feat_dtype == DIC_BF16, f_alias,
                                        ws, st);
   return decoder_backward_impl<float>(*dims, attn_mode, pack, captions, cap_stride, sizes, total, T, B, d_logits,
-                                      d_alphas, alphas, temp, dropout_mask, *grads, d_feats, f_alias, ws, st);
+                                      d_alphas, alphas, temp, dropout_mask, *grads, d_feats, feat_dtype == DIC_BF16,
+                                      f_alias, ws, st);
 }
 
 size_t dic_decode_workspace_bytes(const dic_dims* dims, int dtype, int B, int beam) {

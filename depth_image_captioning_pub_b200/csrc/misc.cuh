@@ -211,12 +211,15 @@ template <typename ST>
 __global__ void __launch_bounds__(256) dfeat_accumulate_kernel(float* __restrict__ dF, const float* __restrict__ alphas,
                                                                const ST* __restrict__ DZ,
                                                                const float* __restrict__ dmeanF, int B, int L, int D,
-                                                               int T, int accumulate) {
+                                                               int T, int accumulate, bf16* __restrict__ out16) {
+  // out16 != null: the final sum is written as bf16 to out16 (annotations are bf16) and dF is only
+  // the fp32 accumulation buffer the GEMM wrote; otherwise dF is updated in place.
   extern __shared__ __align__(16) float al_s[];   // [L][kDfeatTT]
   const int b = blockIdx.y;
   const int d = blockIdx.x * 512 + threadIdx.x * 2;
   const bool active = d < D;
   float* out = dF + (size_t)b * L * D + d;
+  bf16* o16 = out16 ? out16 + (size_t)b * L * D + d : nullptr;
   const float inv_l = 1.f / (float)L;
   for (int t0 = 0; t0 < T; t0 += kDfeatTT) {
     const int tn = min(kDfeatTT, T - t0);
@@ -265,7 +268,10 @@ __global__ void __launch_bounds__(256) dfeat_accumulate_kernel(float* __restrict
             a2.x = fmaf(a.z, dz0[4 * t4 + 2], a2.x); a2.y = fmaf(a.z, dz1[4 * t4 + 2], a2.y);
             a2.x = fmaf(a.w, dz0[4 * t4 + 3], a2.x); a2.y = fmaf(a.w, dz1[4 * t4 + 3], a2.y);
           }
-          *reinterpret_cast<float2*>(out + (size_t)(l0 + r) * D) = a2;
+          if (o16 && t0 + kDfeatTT >= T)
+            *reinterpret_cast<__nv_bfloat162*>(o16 + (size_t)(l0 + r) * D) = __floats2bfloat162_rn(a2.x, a2.y);
+          else
+            *reinterpret_cast<float2*>(out + (size_t)(l0 + r) * D) = a2;
         }
       }
     }
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(256) dfeat_accumulate_kernel(float* __restrict
 
 template <typename ST>
 inline int launch_dfeat_accumulate(float* dF, const float* alphas, const ST* DZ, const float* dmeanF, int B, int L,
-                                   int D, int T, int accumulate, cudaStream_t st) {
+                                   int D, int T, int accumulate, bf16* out16, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DIC_CUDA(cudaFuncSetAttribute(dfeat_accumulate_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -283,7 +289,7 @@ inline int launch_dfeat_accumulate(float* dF, const float* alphas, const ST* DZ,
   ProfScope prof(P_DFEAT, st, 2.0 * (double)B * L * D * sizeof(float));
   dim3 grid(cdiv(D, 512), B);
   dfeat_accumulate_kernel<ST><<<grid, 256, sizeof(float) * L * kDfeatTT, st>>>(dF, alphas, DZ, dmeanF, B, L, D, T,
-                                                                            accumulate);
+                                                                            accumulate, out16);
   DIC_LAUNCH_CHECK();
   return 0;
 }

@@ -118,7 +118,7 @@ class Engine:
         d = self.dims
         B, T = f_rgb.shape[0], len(batch_sizes)
         grads = [torch.empty(s, dtype=torch.float32, device=self.device) for s in param_shapes]
-        d_feats = torch.empty(B, d.L, d.D, dtype=torch.float32, device=self.device) if need_dfeat else None
+        d_feats = torch.empty(B, d.L, d.D, dtype=f_rgb.dtype, device=self.device) if need_dfeat else None
         gs = _params_struct(grads)
         bs = (C.c_int32 * T)(*batch_sizes)
         with torch.cuda.device(self.device):
@@ -221,8 +221,8 @@ class DecoderFunction(torch.autograd.Function):
                                          d_alphas, alphas, ctx.temp, dropout_mask, ctx.ws, ctx.param_shapes,
                                          need_dfeat)
         ctx.ws = None
-        d_rgb = d_feats.to(f_rgb.dtype) if (ctx.needs_input_grad[7] and d_feats is not None) else None
+        d_rgb = d_feats if (ctx.needs_input_grad[7] and d_feats is not None) else None
         d_dep = None
         if ctx.has_depth and ctx.needs_input_grad[8] and d_feats is not None:
-            d_dep = d_feats.to(f_depth.dtype)
+            d_dep = d_feats
         return (None, None, None, None, None, None, None, d_rgb, d_dep, *grads)

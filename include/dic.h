@@ -122,7 +122,7 @@ int dic_decoder_forward(const dic_dims* dims, int dtype, int attn_mode, const vo
  *   d_logits : [sum(bs), V] fp32 gradient of PackedSequence.data
  *   d_alphas : [B,T,L] fp32 gradient of alphas, or NULL
  *   grads    : 17 fp32 buffers in dic_params layout, OVERWRITTEN with the gradients
- *   d_feats  : out [B,L,D] fp32 = dL/d(f_rgb + f_depth) (same tensor for both inputs), or NULL
+ *   d_feats  : out [B,L,D] in feat_dtype = dL/d(f_rgb + f_depth) (same tensor for both inputs), or NULL
  *   f_rgb, f_depth, feat_dtype : the same annotation tensors the forward call received
  *              (when no fused copy was needed the forward kept reading the caller's tensor)
  */
@@ -131,7 +131,7 @@ int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const v
                          const int64_t* captions, int cap_stride, const int32_t* host_batch_sizes,
                          int T, int B, const float* d_logits, const float* d_alphas,
                          const float* alphas, float temp, const float* dropout_mask,
-                         const dic_params* grads, float* d_feats, void* workspace,
+                         const dic_params* grads, void* d_feats, void* workspace,
                          size_t workspace_bytes, void* stream);
 
 /* ---- decoding -----------------------------------------------------------------------
