@@ -185,6 +185,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 

@@ -67,6 +67,25 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = img * KB;
 
+  const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)img * L * A;
+  const int half = lane >> 4, hl = lane & 15;
+  constexpr int RPW = 2 * (kAlphaThreads / 32);      // rows per CTA pass (16)
+  constexpr int IT = 13;                             // 13 * 16 rows >= 196
+
+  // att1 is loop invariant (written once by K0): the first block of its loads is issued BEFORE the
+  // programmatic-dependency wait, so their latency overlaps the tail of the kernel that produces att2.
+  Raw8<ST> raw0[IT];
+  if (A == 128) {
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int l = it * RPW + warp * 2 + half;
+      if (l < L) raw0[it].load_stream(att1 + (size_t)l * A + hl * 8);
+      else raw0[it].zero();
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+
   for (int i = tid; i < A; i += kAlphaThreads) w_s[i] = p.w_full[i];
   for (int i = tid; i < KB * A; i += kAlphaThreads) {
     const int j = i / A, a = i - j * A;
@@ -74,22 +93,22 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
   }
   __syncthreads();
 
-  const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)img * L * A;
   const float b_full = p.b_full[0];
-  const int half = lane >> 4, hl = lane & 15;
-  constexpr int RPW = 2 * (kAlphaThreads / 32);      // rows per CTA pass (16)
   if (A == 128) {
     // Reference shape: one 16-byte load covers a lane's 8 columns.  The whole att1 slab of the image
-    // is put in flight first (kAlphaIters independent loads per thread), then consumed: the kernel is
+    // is put in flight first (IT independent loads per thread), then consumed: the kernel is
     // a pure latency chain otherwise (one 50 KB slab per CTA).
-    constexpr int IT = 13;                            // 13 * 16 rows >= 196
     for (int lb0 = 0; lb0 < L; lb0 += IT * RPW) {
       Raw8<ST> raw[IT];
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
-        const int l = lb0 + it * RPW + warp * 2 + half;
-        if (l < L) raw[it].load_stream(att1 + (size_t)l * A + hl * 8);
-        else raw[it].zero();
+        if (lb0 == 0) {
+          raw[it] = raw0[it];
+        } else {
+          const int l = lb0 + it * RPW + warp * 2 + half;
+          if (l < L) raw[it].load_stream(att1 + (size_t)l * A + hl * 8);
+          else raw[it].zero();
+        }
       }
       float w8[8];
 #pragma unroll
@@ -221,6 +240,9 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
 #pragma unroll
     for (int r = 0; r < kCtxUnroll; ++r) v0[r].load_stream(F + (size_t)(rg + r * kCtxGroups) * D);
   }
+  // the annotations are static; alpha and beta come from the preceding kernels of this step
+  pdl_wait();
+  pdl_trigger();
 
   for (int i = tid; i < KB * L; i += kCtxThreads) {
     const int j = i / L, l = i - j * L;
@@ -335,14 +357,15 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
   }
   {
     ProfScope prof(P_ATTN_ALPHA, st, (double)images * p.L * p.A * sizeof(ST));
-    attn_alpha_kernel<ST, KB><<<images, kAlphaThreads, attn_alpha_smem_bytes(p.L, p.A, KB), st>>>(p);
+    DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, KB>, dim3(images), dim3(kAlphaThreads),
+                        attn_alpha_smem_bytes(p.L, p.A, KB), st, p));
     DIC_LAUNCH_CHECK();
   }
   {
     // algorithmic bytes of the context pass: the annotations once per image-step
     ProfScope prof(P_ATTN_FWD, st, (double)images * p.L * (double)p.D * sizeof(ST));
     dim3 grid(cdiv(p.D, kCtxCols), images);
-    attn_context_kernel<ST, KB><<<grid, kCtxThreads, attn_ctx_smem_bytes(p.L, KB), st>>>(p);
+    DIC_CUDA(launch_pdl(attn_context_kernel<ST, KB>, grid, dim3(kCtxThreads), attn_ctx_smem_bytes(p.L, KB), st, p));
     DIC_LAUNCH_CHECK();
   }
   return 0;
@@ -421,6 +444,8 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
       else v0[r].zero();
     }
   }
+  pdl_wait();       // dzg comes from the preceding GEMM; the annotation loads above are static
+  pdl_trigger();
 
   float dz[8];
 #pragma unroll
@@ -509,6 +534,8 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
   const int tid = threadIdx.x;
   const float* hp = p.hp + (size_t)b * (A + D);
   ST* G = reinterpret_cast<ST*>(p.G) + (size_t)b * p.g_stride;
+  pdl_wait();
+  pdl_trigger();
 
   for (int a = tid; a < A; a += kBwdSmallThreads) {
     w_s[a] = p.w_full[a];
@@ -616,7 +643,7 @@ inline int launch_attn_bwd(const AttnBwdArgs& p, int rows, cudaStream_t st) {
   {
     ProfScope prof(P_ATTN_BWD, st, (double)rows * p.L * (double)p.D * sizeof(ST));
     dim3 grid(chunks, rows);
-    attn_bwd_stream_kernel<ST><<<grid, kCtxThreads, 0, st>>>(p);
+    DIC_CUDA(launch_pdl(attn_bwd_stream_kernel<ST>, grid, dim3(kCtxThreads), 0, st, p));
     DIC_LAUNCH_CHECK();
   }
   {
@@ -626,7 +653,8 @@ inline int launch_attn_bwd(const AttnBwdArgs& p, int rows, cudaStream_t st) {
       attr_set = true;
     }
     ProfScope prof(P_ATTN_BWD_SMALL, st, (double)rows * p.L * p.A * sizeof(ST));
-    attn_bwd_small_kernel<ST><<<rows, kBwdSmallThreads, attn_bwd_small_smem_bytes(p.L, p.A), st>>>(p, chunks);
+    DIC_CUDA(launch_pdl(attn_bwd_small_kernel<ST>, dim3(rows), dim3(kBwdSmallThreads),
+                        attn_bwd_small_smem_bytes(p.L, p.A), st, p, chunks));
     DIC_LAUNCH_CHECK();
   }
   return 0;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -272,5 +273,42 @@ struct StepSizes {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The decoder time loop is a chain of 5-10 short dependent kernels per step.  Launched with the
+// programmatic-stream-serialization attribute, kernel N+1 is scheduled while kernel N is still
+// running: its prologue (shared-memory carve-up, barrier init, TMEM allocation, tensor-map prefetch)
+// overlaps N's tail, and it blocks in pdl_wait() -- before its first access to global memory that N
+// may write or still read -- until N has completed and flushed.  Every kernel in the chain calls
+// pdl_wait() unconditionally, so the ordering guarantees are those of plain stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DIC_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  // event profiling puts event records between the kernels; keep those launches plain
+  return v == 1 && !g_prof.on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace dic

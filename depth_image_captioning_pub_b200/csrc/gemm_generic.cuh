@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(const GemmArgs g) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
 
+  pdl_wait();
+  pdl_trigger();
   const int z = blockIdx.z;
   const int batch = z / g.splits, split = z % g.splits;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -158,10 +160,10 @@ inline int gemm_generic(const GemmArgs& g, cudaStream_t st) {
   const long long tiles128 = (long long)cdiv(g.M, 128) * cdiv(g.N, 128) * g.batch * g.splits;
   if (tiles128 >= 148 && g.M >= 128 && g.N >= 128) {
     dim3 grid(cdiv(g.N, 128), cdiv(g.M, 128), g.batch * g.splits);
-    gemm_generic_kernel<128, 128, 16><<<grid, 256, 0, st>>>(g);
+    DIC_CUDA(launch_pdl(gemm_generic_kernel<128, 128, 16>, grid, dim3(256), 0, st, g));
   } else {
     dim3 grid(cdiv(g.N, 64), cdiv(g.M, 64), g.batch * g.splits);
-    gemm_generic_kernel<64, 64, 32><<<grid, 256, 0, st>>>(g);
+    DIC_CUDA(launch_pdl(gemm_generic_kernel<64, 64, 32>, grid, dim3(256), 0, st, g));
   }
   DIC_LAUNCH_CHECK();
   return 0;

@@ -195,6 +195,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous
+  // kernel's tail; operands and the output buffer may only be touched after it has completed.
+  pdl_wait();
+  pdl_trigger();
 
   // tile index -> (split, m block, n block); n fastest so that concurrent CTAs share the A tile in L2
   auto decode = [&](int t, int& split, int& m0, int& n0, int& kb0, int& kb1) {
@@ -475,7 +479,8 @@ inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                                   (int)tc_smem_bytes<BN>()));
     attr_set = true;
   }
-  tc_gemm_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, tc_smem_bytes<BN>(), st>>>(tmA, tmB, p);
+  DIC_CUDA(launch_pdl(tc_gemm_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kTcThreads), tc_smem_bytes<BN>(), st, tmA, tmB,
+                      p));
   DIC_LAUNCH_CHECK();
   return 0;
 }

@@ -25,6 +25,8 @@ struct LstmFwdArgs {
 
 template <typename ST>
 __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= p.rows * p.H) return;
   const int r = idx / p.H, j = idx - r * p.H;
@@ -70,7 +72,7 @@ template <typename ST>
 inline int launch_lstm_fwd(const LstmFwdArgs& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
   ProfScope prof(P_LSTM, st);
-  lstm_fwd_kernel<ST><<<cdiv(p.rows * p.H, 256), 256, 0, st>>>(p);
+  DIC_CUDA(launch_pdl(lstm_fwd_kernel<ST>, dim3(cdiv(p.rows * p.H, 256)), dim3(256), 0, st, p));
   DIC_LAUNCH_CHECK();
   return 0;
 }
@@ -91,6 +93,8 @@ struct LstmBwdArgs {
 
 template <typename ST>
 __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= p.rows * p.H) return;
   const int r = idx / p.H, j = idx - r * p.H;
@@ -115,7 +119,7 @@ template <typename ST>
 inline int launch_lstm_bwd(const LstmBwdArgs& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
   ProfScope prof(P_LSTM, st);
-  lstm_bwd_kernel<ST><<<cdiv(p.rows * p.H, 256), 256, 0, st>>>(p);
+  DIC_CUDA(launch_pdl(lstm_bwd_kernel<ST>, dim3(cdiv(p.rows * p.H, 256)), dim3(256), 0, st, p));
   DIC_LAUNCH_CHECK();
   return 0;
 }
