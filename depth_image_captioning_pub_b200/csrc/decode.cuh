@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(256) argmax_embed_kernel(const float* __restri
   __shared__ float sv[8];
   __shared__ int si[8];
   __shared__ int s_tok;
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   const float* lg = logits + (size_t)r * V;
   float best = -INFINITY;
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(256) argmax_embed_kernel(const float* __restri
 __global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ logits, int V,
                                                       float* __restrict__ lse) {
   __shared__ float scratch[64];
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   const float* lg = logits + (size_t)r * V;
   float m = -INFINITY;
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict_
   __shared__ float wv[8];
   __shared__ int wi[8];
   __shared__ int s_win;
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < K) {
@@ -185,8 +191,8 @@ inline int launch_beam_topk(const float* scores, const uint8_t* finished, const 
   if (K > V) DIC_FAIL(-4, "beam %d larger than vocabulary %d", K, V);
 #define DIC_TOPK_CASE(KK)                                                                       \
   case KK:                                                                                      \
-    beam_topk_kernel<KK><<<B, 256, 0, st>>>(scores, finished, logits, lse, V, end_id, new_scores, \
-                                            back, tok, new_finished);                           \
+    DIC_CUDA(launch_pdl(beam_topk_kernel<KK>, dim3(B), dim3(256), 0, st, scores, finished, logits, lse, V, \
+                        end_id, new_scores, back, tok, new_finished));                          \
     break;
   switch (K) {
     DIC_TOPK_CASE(1) DIC_TOPK_CASE(2) DIC_TOPK_CASE(3) DIC_TOPK_CASE(4)
@@ -208,6 +214,8 @@ __global__ void __launch_bounds__(256) beam_reorder_kernel(const ST* __restrict_
                                                            ST* __restrict__ Xnext, long long x_row, int col_h,
                                                            float* __restrict__ c, int rows, int K, int E,
                                                            int H) {
+  pdl_wait();
+  pdl_trigger();
   const int W = E + H;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < rows * W; i += gridDim.x * 256) {
     const int r = i / W, q = i - r * W;

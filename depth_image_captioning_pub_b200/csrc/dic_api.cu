@@ -294,6 +294,10 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   }
 
   const float inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
+  float* dh_part = reinterpret_cast<float*>(ws + lay.dh_part);
+  int dh_splits = cdiv((int)GW, kTcBK) / 4;      // >= 4 k-blocks of 64 per split
+  if (dh_splits > kDhSplitsMax) dh_splits = kDhSplitsMax;
+  if (dh_splits < 1) dh_splits = 1;
   int off = total;
   for (int t = T - 1; t >= 0; --t) {
     const int n = sizes.n[t];
@@ -303,7 +307,9 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 
     LstmBwdArgs lb;
     memset(&lb, 0, sizeof(lb));
-    lb.dh_carry = dh; lb.dh_out = dHout + (size_t)off * H;
+    lb.dh_carry = dh_part; lb.dh_stride = (long long)B * H; lb.dh_splits = dh_splits;
+    lb.dh_rows = (t + 1 < T) ? sizes.n[t + 1] : 0;       // rows that were active one step later
+    lb.dh_out = dHout + (size_t)off * H;
     lb.mask = dropout_mask ? dropout_mask + (size_t)off * H : nullptr;
     lb.dc_carry = dc;
     lb.acts = acts + (size_t)t * B * 4 * H;
@@ -317,7 +323,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
       GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, reinterpret_cast<const ST*>(pk.Wg()) + E, is_bf16, 0, dzg,
                                 0, D, n, D, 4 * H, nullptr);
       g.b_n = 1; g.b_k = XW;
-      DIC_TRY(gemm_splitk(g, st));
+      DIC_TRY(gemm(g, st));     // no split-K here: a memset node would break the PDL kernel chain
     }
 
     AttnBwdArgs ab;
@@ -339,11 +345,20 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 
     // dh_{t-1} = [dgates | datt2 | dbeta'] . [W_hh ; W_dec ; W_beta]
     {
-      GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, pk.Whdb(), is_bf16, 0, dh, 0, H, n, H, (int)GW, nullptr);
+      // K = 4H+A+D is long and the output tiny: split-K into partial buffers that the next
+      // lstm_bwd (and the final reduce) sum in a fixed order -- no memset, no atomics
+      GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, pk.Whdb(), is_bf16, 0, dh_part, 0, H, n, H, (int)GW, nullptr);
       g.b_n = 1; g.b_k = H;
-      DIC_TRY(gemm_splitk(g, st));   // zero-fills and accumulates only the n valid rows
+      g.splits = dh_splits;
+      g.split_mode = 1;
+      g.split_stride = (long long)B * H;
+      DIC_TRY(gemm(g, st));
     }
   }
+  // dh0 (rows [0, bs_valid[0]) = all B rows)
+  DIC_CUDA(launch_pdl(reduce_parts_kernel, dim3(cdiv(B * H, 256)), dim3(256), 0, st, (const float*)dh_part,
+                      (long long)B * H, dh_splits, dh, B * H));
+  DIC_LAUNCH_CHECK();
 
   // ---- post-loop: everything that is a sum over (t, b) is one contraction over T*B rows ----
   // init_linear: rows [0,H) from dh0, rows [H,2H) from dc0
@@ -362,10 +377,15 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   }
 
   // biases of the LSTM / decoder_att / f_beta: column sums of G
-  DIC_TRY(launch_colsum(G, is_bf16, (int)TB, 4 * H, GW, gr.b_ih, st));
-  DIC_CUDA(cudaMemcpyAsync(gr.b_hh, gr.b_ih, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
-  DIC_TRY(launch_colsum(G + 4 * H, is_bf16, (int)TB, A, GW, gr.dec_att_b, st));
-  DIC_TRY(launch_colsum(G + 4 * H + A, is_bf16, (int)TB, D, GW, gr.fbeta_b, st));
+  // (one pass over G, then the four slices are copied out)
+  {
+    float* gsum = reinterpret_cast<float*>(ws + lay.tmpvec);
+    DIC_TRY(launch_colsum(G, is_bf16, (int)TB, (int)GW, GW, gsum, st));
+    DIC_CUDA(cudaMemcpyAsync(gr.b_ih, gsum, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+    DIC_CUDA(cudaMemcpyAsync(gr.b_hh, gsum, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+    DIC_CUDA(cudaMemcpyAsync(gr.dec_att_b, gsum + 4 * H, sizeof(float) * A, cudaMemcpyDeviceToDevice, st));
+    DIC_CUDA(cudaMemcpyAsync(gr.fbeta_b, gsum + 4 * H + A, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  }
 
   auto wgrad = [&](const ST* Aop, long long a_ld, int M, const ST* Bop, long long b_ld, int N, int K,
                    float* C, long long ldc) -> int {
@@ -410,7 +430,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     GemmArgs g = gemm_args_nt(dl, dl_bf16, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
     g.a_m = 1; g.a_k = V; g.b_n = 1; g.b_k = H;
     DIC_TRY(gemm_splitk(g, st));
-    DIC_TRY(launch_colsum(d_logits, 0, total, V, V, gr.lin_b, st));
+    DIC_TRY(launch_colsum(dl, dl_bf16, total, V, V, gr.lin_b, st));   // bf16 mode: half the bytes
   }
 
   // dL/dF = datt1 . W_enc + sum_t alpha_t (x) dz_t + dmeanF / L
@@ -509,19 +529,20 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
     DIC_TRY(gemm(g, st));
 
     if (!beam) {
-      argmax_embed_kernel<ST><<<R, 256, 0, st>>>(lg, V, tokens + t, max_len,
-                                                 reinterpret_cast<const ST*>(pk.Emb()), E, Xn, XW);
+      DIC_CUDA(launch_pdl(argmax_embed_kernel<ST>, dim3(R), dim3(256), 0, st, lg, V, tokens + t, (long long)max_len,
+                          reinterpret_cast<const ST*>(pk.Emb()), E, Xn, XW));
       DIC_LAUNCH_CHECK();
     } else {
       float* lse_t = lse_out ? lse_out + (size_t)t * R : lse_ws;
-      row_lse_kernel<<<R, 256, 0, st>>>(lg, V, lse_t);
+      DIC_CUDA(launch_pdl(row_lse_kernel, dim3(R), dim3(256), 0, st, (const float*)lg, V, lse_t));
       DIC_LAUNCH_CHECK();
       int32_t* back_t = back_ws + (size_t)t * R;
       int32_t* tok_t = tok_ws + (size_t)t * R;
       DIC_TRY(launch_beam_topk(sc[t & 1], fin[t & 1], lg, lse_t, B, K, V, end_id, sc[(t + 1) & 1], back_t,
                                tok_t, fin[(t + 1) & 1], st));
-      beam_reorder_kernel<ST><<<cdiv(R * (E + H), 256), 256, 0, st>>>(
-          h_tmp, c_tmp, back_t, tok_t, reinterpret_cast<const ST*>(pk.Emb()), Xn, XW, E + D, c, R, K, E, H);
+      DIC_CUDA(launch_pdl(beam_reorder_kernel<ST>, dim3(cdiv(R * (E + H), 256)), dim3(256), 0, st, (const ST*)h_tmp,
+                          (const float*)c_tmp, (const int32_t*)back_t, (const int32_t*)tok_t,
+                          reinterpret_cast<const ST*>(pk.Emb()), Xn, XW, E + D, c, R, K, E, H));
       DIC_LAUNCH_CHECK();
       if (step_scores_out)
         DIC_CUDA(cudaMemcpyAsync(step_scores_out + (size_t)t * R, sc[(t + 1) & 1], sizeof(float) * R,

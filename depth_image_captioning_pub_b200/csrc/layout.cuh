@@ -70,11 +70,12 @@ struct Pack {
 };
 
 constexpr int kGateSplitsMax = 16;
+constexpr int kDhSplitsMax = 10;     // split-K partial buffers of the per-step dh GEMM (<= 16)
 
 // Training workspace (forward state saved for backward + backward scratch).
 struct TrainLayout {
   size_t Fsum, meanF, att1, XH, HP, Z, acts, c_all, gate_part, Hdrop;
-  size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16, dal_part, h0, dF32;
+  size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16, dal_part, h0, dF32, dh_part;
   size_t bytes;
   size_t XW, GW;
   int es;
@@ -110,6 +111,7 @@ struct TrainLayout {
     dlogits16 = c.take(dtype == DIC_BF16 ? TB * d.V * 2 : 16);   // bf16 copy of d_logits (GEMM operand)
     dal_part = c.take(sizeof(float) * (size_t)((d.D + 255) / 256) * B * d.L);   // per-chunk dalpha partials
     h0 = c.take(sizeof(float) * B * d.H);
+    dh_part = c.take(sizeof(float) * kDhSplitsMax * B * d.H);
     dF32 = c.take(sizeof(float) * (size_t)B * d.L * d.D);   // fp32 dL/dF accumulator when annotations are bf16
     bytes = c.off;
   }

@@ -79,7 +79,10 @@ inline int launch_lstm_fwd(const LstmFwdArgs& p, cudaStream_t st) {
 
 // Backward through the cell for the first `rows` (valid) batch rows of one step.
 struct LstmBwdArgs {
-  const float* dh_carry;  // [B,H] from step t+1 (W_hh, f_beta, decoder_att paths)
+  const float* dh_carry;  // [splits][B,H] split-K partials of dh from step t+1 (W_hh, f_beta, decoder_att paths)
+  long long dh_stride;    // elements between partials
+  int dh_splits;          // number of partials
+  int dh_rows;            // rows [0, dh_rows) carry a gradient from step t+1 (bs_valid of t+1); others 0
   const float* dh_out;    // [rows,H] d(logits).W_out for this step's packed rows
   const float* mask;      // [rows,H] dropout mask or null
   float* dc_carry;        // [B,H] in/out
@@ -102,7 +105,18 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
   const float* a = p.acts + (size_t)r * 4 * H;
   const float ig = a[j], fg = a[H + j], gg = a[2 * H + j], og = a[3 * H + j];
   const float m = p.mask ? p.mask[idx] : 1.f;
-  const float dh = p.dh_carry[idx] + p.dh_out[idx] * m;
+  float dh = p.dh_out[idx] * m;
+  if (r < p.dh_rows) {
+    constexpr int kMaxSplits = 16;
+    float part[kMaxSplits];
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplits; ++sp)
+      part[sp] = sp < p.dh_splits ? p.dh_carry[(size_t)sp * p.dh_stride + idx] : 0.f;
+    float carry = 0.f;
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplits; ++sp) carry += part[sp];
+    dh += carry;
+  }
   const float tc = tanhf(p.c_new[idx]);
   const float dc = p.dc_carry[idx] + dh * og * (1.f - tc * tc);
   const float d_o = dh * tc;
@@ -113,6 +127,17 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
   G[H + j] = from_f<ST>(d_f * fg * (1.f - fg));
   G[2 * H + j] = from_f<ST>(d_g * (1.f - gg * gg));
   G[3 * H + j] = from_f<ST>(d_o * og * (1.f - og));
+}
+
+// out[i] = sum_s parts[s][i]  (final dh0 after the time loop)
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restrict__ parts, long long stride, int splits,
+                                                           float* __restrict__ out, int n) {
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += parts[(size_t)sp * stride + i];
+  out[i] = s;
 }
 
 template <typename ST>
