@@ -75,7 +75,8 @@ PROTOTYPES = {
     "dic_attention_workspace_bytes": (_SZ, [_DP, _I, _I]),
     "dic_attention_forward": (_I, [_DP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _F, _P, _P, _P,
                                    _SZ, _P]),
-    "dic_beam_select": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "dic_beam_select_workspace_bytes": (_SZ, [_I, _I]),
+    "dic_beam_select": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "dic_row_lse": (_I, [_P, _I, _I, _P, _P]),
     "dic_gemm_nt": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
     "dic_gemm_ex": (_I, [_I, _I, _I, _I, _P, _I, C.c_longlong, C.c_longlong, _P, _I, C.c_longlong, C.c_longlong,

@@ -91,70 +91,74 @@ __global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ 
 // cand[j*V+v] = scores[j] + (logits[j,v] - lse[j]); finished rows keep only <end> at cost 0.
 // Stable top-K: order by (value desc, flat index asc) -- bit-exact w.r.t. the oracle's
 // beam_select given identical inputs (plain fp32 add/sub, round-to-nearest, no contraction).
-struct Cand {
-  float v;
-  int i;
-};
+//
+// Two kernels.  (1) beam_row_topk_kernel: one CTA per beam ROW computes the row's log-sum-exp
+// (unless given) and its own top-K candidates; (2) beam_merge_kernel: one warp per image merges
+// the K*K row candidates.  The top-K of the union of per-row top-Ks under one total order IS the
+// global top-K, so the result is identical to a single pass over all K*V candidates -- which is
+// what the first version did with one CTA per image and took 118 us per step (ncu launch list,
+// profiles/): 128 CTAs cannot scan 6.4 M candidates quickly.
 __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) {
   return v > bv || (v == bv && i < bi);
 }
 
 template <int K>
-__global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict__ scores,
-                                                        const uint8_t* __restrict__ finished,
-                                                        const float* __restrict__ logits,
-                                                        const float* __restrict__ lse, int V, int end_id,
-                                                        float* __restrict__ new_scores,
-                                                        int32_t* __restrict__ back, int32_t* __restrict__ tok,
-                                                        uint8_t* __restrict__ new_finished) {
-  __shared__ float s_sc[K], s_lse[K];
-  __shared__ uint8_t s_fin[K];
+__global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restrict__ scores,
+                                                            const uint8_t* __restrict__ finished,
+                                                            const float* __restrict__ logits,
+                                                            const float* __restrict__ lse_in,
+                                                            float* __restrict__ lse_out, int V, int end_id,
+                                                            float* __restrict__ cand_v, int* __restrict__ cand_i) {
+  __shared__ float scratch[64];
   __shared__ float wv[8];
   __shared__ int wi[8];
   __shared__ int s_win;
   pdl_wait();
   pdl_trigger();
-  const int b = blockIdx.x;
+  const int r = blockIdx.x;            // global row = b*K + j
+  const int j = r % K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < K) {
-    s_sc[tid] = scores[b * K + tid];
-    s_lse[tid] = lse[b * K + tid];
-    s_fin[tid] = finished[b * K + tid];
+  const float* lg = logits + (size_t)r * V;
+  float ls;
+  if (lse_in) {
+    ls = lse_in[r];
+  } else {
+    float m = -INFINITY;
+    for (int v = tid; v < V; v += 256) m = fmaxf(m, lg[v]);
+    m = block_max(m, scratch);
+    float s = 0.f;
+    for (int v = tid; v < V; v += 256) s += expf(lg[v] - m);
+    s = block_sum(s, scratch);
+    ls = m + logf(s);
   }
-  __syncthreads();
+  if (tid == 0 && lse_out) lse_out[r] = ls;
+  const float sc = scores[r];
+  const bool fin = finished[r] != 0;
 
   float lv[K];
   int li[K];
 #pragma unroll
   for (int q = 0; q < K; ++q) { lv[q] = -INFINITY; li[q] = 0x7fffffff; }
-
-  for (int j = 0; j < K; ++j) {
-    const float sc = s_sc[j], ls = s_lse[j];
-    const bool fin = s_fin[j] != 0;
-    const float* lg = logits + ((size_t)b * K + j) * V;
-    for (int v = tid; v < V; v += 256) {
-      float c;
-      if (fin) c = (v == end_id) ? sc : -INFINITY;
-      else c = __fadd_rn(sc, __fsub_rn(lg[v], ls));
-      const int fi = j * V + v;
-      if (cand_better(c, fi, lv[K - 1], li[K - 1])) {
-        lv[K - 1] = c; li[K - 1] = fi;
+  for (int v = tid; v < V; v += 256) {
+    float c;
+    if (fin) c = (v == end_id) ? sc : -INFINITY;
+    else c = __fadd_rn(sc, __fsub_rn(lg[v], ls));
+    const int fi = j * V + v;
+    if (cand_better(c, fi, lv[K - 1], li[K - 1])) {
+      lv[K - 1] = c; li[K - 1] = fi;
 #pragma unroll
-        for (int q = K - 1; q > 0; --q) {
-          if (cand_better(lv[q], li[q], lv[q - 1], li[q - 1])) {
-            const float tv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = tv;
-            const int ti = li[q]; li[q] = li[q - 1]; li[q - 1] = ti;
-          }
+      for (int q = K - 1; q > 0; --q) {
+        if (cand_better(lv[q], li[q], lv[q - 1], li[q - 1])) {
+          const float tv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = tv;
+          const int ti = li[q]; li[q] = li[q - 1]; li[q - 1] = ti;
         }
       }
     }
   }
-
   // K rounds of block-wide arg-best over the heads of the per-thread sorted lists
-  for (int r = 0; r < K; ++r) {
-    float hv = lv[0];
-    int hi = li[0];
-    float bv = hv;
+  for (int rd = 0; rd < K; ++rd) {
+    const int hi = li[0];
+    float bv = lv[0];
     int bi = hi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -168,14 +172,11 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict_
       for (int w = 1; w < 8; ++w)
         if (cand_better(wv[w], wi[w], bv, bi)) { bv = wv[w]; bi = wi[w]; }
       s_win = bi;
-      const int jb = bi / V, tk = bi - jb * V;
-      new_scores[b * K + r] = bv;
-      back[b * K + r] = jb;
-      tok[b * K + r] = tk;
-      new_finished[b * K + r] = (uint8_t)((s_fin[jb] != 0) || (tk == end_id));
+      cand_v[(size_t)r * K + rd] = bv;
+      cand_i[(size_t)r * K + rd] = bi;
     }
     __syncthreads();
-    if (hi == s_win) {  // pop the winner's head (flat indices are unique)
+    if (hi == s_win && hi != 0x7fffffff) {  // pop the winner's head (flat indices are unique)
 #pragma unroll
       for (int q = 0; q < K - 1; ++q) { lv[q] = lv[q + 1]; li[q] = li[q + 1]; }
       lv[K - 1] = -INFINITY; li[K - 1] = 0x7fffffff;
@@ -184,15 +185,64 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict_
   }
 }
 
-inline int launch_beam_topk(const float* scores, const uint8_t* finished, const float* logits,
-                            const float* lse, int B, int K, int V, int end_id, float* new_scores,
-                            int32_t* back, int32_t* tok, uint8_t* new_finished, cudaStream_t st) {
+// one warp per image: merge the K sorted row lists (K*K <= 64 candidates, two per lane)
+template <int K>
+__global__ void __launch_bounds__(128) beam_merge_kernel(const float* __restrict__ cand_v,
+                                                         const int* __restrict__ cand_i,
+                                                         const uint8_t* __restrict__ finished, int B, int V,
+                                                         int end_id, float* __restrict__ new_scores,
+                                                         int32_t* __restrict__ back, int32_t* __restrict__ tok,
+                                                         uint8_t* __restrict__ new_finished) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  constexpr int N = K * K;
+  float v0 = -INFINITY, v1 = -INFINITY;
+  int i0 = 0x7fffffff, i1 = 0x7fffffff;
+  if (lane < N) { v0 = cand_v[(size_t)b * N + lane]; i0 = cand_i[(size_t)b * N + lane]; }
+  if (lane + 32 < N) { v1 = cand_v[(size_t)b * N + lane + 32]; i1 = cand_i[(size_t)b * N + lane + 32]; }
+  for (int rd = 0; rd < K; ++rd) {
+    float bv = v0;
+    int bi = i0;
+    if (cand_better(v1, i1, bv, bi)) { bv = v1; bi = i1; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      const int jb = bi / V, tk = bi - jb * V;
+      new_scores[b * K + rd] = bv;
+      back[b * K + rd] = jb;
+      tok[b * K + rd] = tk;
+      new_finished[b * K + rd] = (uint8_t)((finished[b * K + jb] != 0) || (tk == end_id));
+    }
+    if (i0 == bi && bi != 0x7fffffff) { v0 = -INFINITY; i0 = 0x7fffffff; }
+    if (i1 == bi && bi != 0x7fffffff) { v1 = -INFINITY; i1 = 0x7fffffff; }
+  }
+}
+
+inline size_t beam_select_workspace_bytes(int B, int K) { return (size_t)B * K * K * (sizeof(float) + sizeof(int)); }
+
+// lse_in != null: use the given row log-sum-exps; else compute them (and write lse_out if given)
+inline int launch_beam_select(const float* scores, const uint8_t* finished, const float* logits,
+                              const float* lse_in, float* lse_out, int B, int K, int V, int end_id,
+                              void* workspace, float* new_scores, int32_t* back, int32_t* tok,
+                              uint8_t* new_finished, cudaStream_t st) {
   if (B <= 0) return 0;
   if (K > V) DIC_FAIL(-4, "beam %d larger than vocabulary %d", K, V);
-#define DIC_TOPK_CASE(KK)                                                                       \
-  case KK:                                                                                      \
-    DIC_CUDA(launch_pdl(beam_topk_kernel<KK>, dim3(B), dim3(256), 0, st, scores, finished, logits, lse, V, \
-                        end_id, new_scores, back, tok, new_finished));                          \
+  float* cv = reinterpret_cast<float*>(workspace);
+  int* ci = reinterpret_cast<int*>(cv + (size_t)B * K * K);
+#define DIC_TOPK_CASE(KK)                                                                                  \
+  case KK:                                                                                                 \
+    DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK>, dim3(B * KK), dim3(256), 0, st, scores, finished, logits, \
+                        lse_in, lse_out, V, end_id, cv, ci));                                              \
+    DIC_LAUNCH_CHECK();                                                                                    \
+    DIC_CUDA(launch_pdl(beam_merge_kernel<KK>, dim3(cdiv(B, 4)), dim3(128), 0, st, (const float*)cv,       \
+                        (const int*)ci, finished, B, V, end_id, new_scores, back, tok, new_finished));     \
     break;
   switch (K) {
     DIC_TOPK_CASE(1) DIC_TOPK_CASE(2) DIC_TOPK_CASE(3) DIC_TOPK_CASE(4)

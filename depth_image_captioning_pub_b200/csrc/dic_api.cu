@@ -534,12 +534,11 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       DIC_LAUNCH_CHECK();
     } else {
       float* lse_t = lse_out ? lse_out + (size_t)t * R : lse_ws;
-      DIC_CUDA(launch_pdl(row_lse_kernel, dim3(R), dim3(256), 0, st, (const float*)lg, V, lse_t));
-      DIC_LAUNCH_CHECK();
       int32_t* back_t = back_ws + (size_t)t * R;
       int32_t* tok_t = tok_ws + (size_t)t * R;
-      DIC_TRY(launch_beam_topk(sc[t & 1], fin[t & 1], lg, lse_t, B, K, V, end_id, sc[(t + 1) & 1], back_t,
-                               tok_t, fin[(t + 1) & 1], st));
+      // row log-sum-exp + per-row top-K in one kernel, then a per-image merge
+      DIC_TRY(launch_beam_select(sc[t & 1], fin[t & 1], lg, nullptr, lse_t, B, K, V, end_id, ws + lay.cand,
+                                 sc[(t + 1) & 1], back_t, tok_t, fin[(t + 1) & 1], st));
       DIC_CUDA(launch_pdl(beam_reorder_kernel<ST>, dim3(cdiv(R * (E + H), 256)), dim3(256), 0, st, (const ST*)h_tmp,
                           (const float*)c_tmp, (const int32_t*)back_t, (const int32_t*)tok_t,
                           reinterpret_cast<const ST*>(pk.Emb()), Xn, XW, E + D, c, R, K, E, H));
@@ -855,13 +854,20 @@ int dic_attention_forward(const dic_dims* dims, int dtype, int attn_mode, const 
                                        temp, context, alpha, ws, st);
 }
 
+size_t dic_beam_select_workspace_bytes(int B, int K) {
+  if (B <= 0 || K <= 0) return 0;
+  return beam_select_workspace_bytes(B, K);
+}
+
 int dic_beam_select(const float* scores, const uint8_t* finished, const float* logits, const float* lse, int B,
                     int K, int V, int end_id, float* new_scores, int32_t* back, int32_t* tok,
-                    uint8_t* new_finished, void* stream) {
-  if (!scores || !finished || !logits || !lse || !new_scores || !back || !tok || !new_finished)
+                    uint8_t* new_finished, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!scores || !finished || !logits || !lse || !new_scores || !back || !tok || !new_finished || !workspace)
     DIC_FAIL(-1, "null argument");
-  return launch_beam_topk(scores, finished, logits, lse, B, K, V, end_id, new_scores, back, tok, new_finished,
-                          reinterpret_cast<cudaStream_t>(stream));
+  if (B <= 0 || K <= 0 || K > DIC_MAX_BEAM) DIC_FAIL(-1, "bad B/K");
+  if (workspace_bytes < beam_select_workspace_bytes(B, K)) DIC_FAIL(-1, "workspace too small");
+  return launch_beam_select(scores, finished, logits, lse, nullptr, B, K, V, end_id, workspace, new_scores, back,
+                            tok, new_finished, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dic_row_lse(const float* logits, int R, int V, float* lse, void* stream) {

@@ -120,7 +120,7 @@ struct TrainLayout {
 // Decode workspace: R = B*beam rows.
 struct DecodeLayout {
   size_t Fsum, meanF, att1, XH, HP, c, c_tmp, h_tmp, h0, c0, gate_part, logits, lse;
-  size_t scores, scores2, fin, fin2, back, tok, step_scores, alpha;
+  size_t scores, scores2, fin, fin2, back, tok, step_scores, alpha, cand;
   size_t bytes;
   size_t XW;
   int es;
@@ -150,6 +150,7 @@ struct DecodeLayout {
     tok = c_.take(sizeof(int32_t) * R * max_len);
     step_scores = c_.take(sizeof(float) * R * max_len);
     alpha = c_.take(sizeof(float) * R * d.L);
+    cand = c_.take(R * beam * (sizeof(float) + sizeof(int)));     // per-row top-K candidates
     bytes = c_.off;
   }
 };

@@ -178,9 +178,11 @@ int dic_attention_forward(const dic_dims* dims, int dtype, int attn_mode, const 
  * beam_select given identical inputs): scores [B,K] fp32, finished [B,K] uint8,
  * logits [B*K,V] fp32, lse [B*K] fp32 -> new_scores [B,K], back [B,K] int32, tok [B,K] int32,
  * new_finished [B,K] uint8.  cand = scores + (logits - lse), stable top-K, ties -> lowest index. */
+size_t dic_beam_select_workspace_bytes(int B, int K);
 int dic_beam_select(const float* scores, const uint8_t* finished, const float* logits,
                     const float* lse, int B, int K, int V, int end_id, float* new_scores,
-                    int32_t* back, int32_t* tok, uint8_t* new_finished, void* stream);
+                    int32_t* back, int32_t* tok, uint8_t* new_finished, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* Row-wise log-sum-exp of logits [R,V] fp32 -> lse [R] fp32. */
 int dic_row_lse(const float* logits, int R, int V, float* lse, void* stream);

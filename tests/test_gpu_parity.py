@@ -348,9 +348,11 @@ def test_beam_select_bit_exact(B, K, V, cuda_device):
         o_b = torch.empty(B, K, dtype=torch.int32, device=dev)
         o_t = torch.empty(B, K, dtype=torch.int32, device=dev)
         o_f = torch.empty(B, K, dtype=torch.uint8, device=dev)
+        wsz = lib.dic_beam_select_workspace_bytes(B, K)
+        wsb = torch.empty(wsz, dtype=torch.uint8, device=dev)
         _lib.check(lib.dic_beam_select(sc.to(dev).data_ptr(), fin_in.data_ptr(), lg.data_ptr(), lse.data_ptr(), B, K,
                                        V, end_id, o_s.data_ptr(), o_b.data_ptr(), o_t.data_ptr(), o_f.data_ptr(),
-                                       _lib.stream_ptr(dev)))
+                                       wsb.data_ptr(), wsz, _lib.stream_ptr(dev)))
         np.testing.assert_array_equal(o_b.cpu().numpy(), back.numpy().astype(np.int32))
         np.testing.assert_array_equal(o_t.cpu().numpy(), tok.numpy().astype(np.int32))
         np.testing.assert_array_equal(o_f.cpu().numpy().astype(bool), nf.numpy())
