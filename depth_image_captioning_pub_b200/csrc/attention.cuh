@@ -23,7 +23,7 @@
 
 namespace dic {
 
-constexpr int kAlphaThreads = 256;
+constexpr int kAlphaThreads = 512;
 constexpr int kCtxThreads = 128;
 constexpr int kCtxCols = 256;                       // columns per context CTA (32 lanes x 8)
 constexpr int kCtxGroups = kCtxThreads / 32;        // 4 row groups (one warp each)
@@ -44,6 +44,7 @@ struct AttnFwdArgs {
   int L, D, A;
   int mode;
   float inv_temp;
+  int rpi;              // rows (beams) per image for the alpha kernel's row -> image map (0 = KB)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -63,24 +64,26 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
   float* e_s = att2_s + KB * p.A;            // [KB][Lp]
   const int L = p.L, D = p.D, A = p.A;
   const int Lp = (L + 3) & ~3;
-  const int img = blockIdx.x;
+  // KB rows of one image per CTA, or (rpi > 0, KB == 1) one row per CTA with rpi rows sharing an image:
+  // beam decoding at 128 images per GPU needs the 5x larger grid more than it needs the att1 reuse
+  const int img = p.rpi > 0 ? blockIdx.x / p.rpi : blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row0 = img * KB;
+  const int row0 = p.rpi > 0 ? blockIdx.x : img * KB;
 
   const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)img * L * A;
   const int half = lane >> 4, hl = lane & 15;
-  constexpr int RPW = 2 * (kAlphaThreads / 32);      // rows per CTA pass (16)
-  constexpr int IT = 13;                             // 13 * 16 rows >= 196
+  constexpr int RPW = 2 * (kAlphaThreads / 32);      // rows per CTA pass (32)
+  constexpr int IT = 7;                              // 7 * 32 rows >= 196: 7 x 16-byte loads per thread
 
   // att1 is loop invariant (written once by K0): the first block of its loads is issued BEFORE the
   // programmatic-dependency wait, so their latency overlaps the tail of the kernel that produces att2.
-  Raw8<ST> raw0[IT];
+  Raw8<ST> raw[IT];
   if (A == 128) {
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
       const int l = it * RPW + warp * 2 + half;
-      if (l < L) raw0[it].load_stream(att1 + (size_t)l * A + hl * 8);
-      else raw0[it].zero();
+      if (l < L) raw[it].load_stream(att1 + (size_t)l * A + hl * 8);
+      else raw[it].zero();
     }
   }
   pdl_wait();
@@ -98,21 +101,18 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
     // Reference shape: one 16-byte load covers a lane's 8 columns.  The whole att1 slab of the image
     // is put in flight first (IT independent loads per thread), then consumed: the kernel is
     // a pure latency chain otherwise (one 50 KB slab per CTA).
-    for (int lb0 = 0; lb0 < L; lb0 += IT * RPW) {
-      Raw8<ST> raw[IT];
+    float w8[8];
 #pragma unroll
-      for (int it = 0; it < IT; ++it) {
-        if (lb0 == 0) {
-          raw[it] = raw0[it];
-        } else {
+    for (int q = 0; q < 8; ++q) w8[q] = w_s[hl * 8 + q];
+    for (int lb0 = 0; lb0 < L; lb0 += IT * RPW) {
+      if (lb0 > 0) {      // L > 208: reload the (single) register block for the next 208 rows
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
           const int l = lb0 + it * RPW + warp * 2 + half;
           if (l < L) raw[it].load_stream(att1 + (size_t)l * A + hl * 8);
           else raw[it].zero();
         }
       }
-      float w8[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) w8[q] = w_s[hl * 8 + q];
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
         const int l = lb0 + it * RPW + warp * 2 + half;
@@ -351,14 +351,17 @@ template <typename ST, int KB>
 inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DIC_CUDA(cudaFuncSetAttribute(attn_alpha_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DIC_CUDA(cudaFuncSetAttribute(attn_alpha_kernel<ST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     DIC_CUDA(cudaFuncSetAttribute(attn_context_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
   {
+    // one CTA per ROW (beam): images*KB CTAs, the KB CTAs of an image share its att1 slab through L2
     ProfScope prof(P_ATTN_ALPHA, st, (double)images * p.L * p.A * sizeof(ST));
-    DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, KB>, dim3(images), dim3(kAlphaThreads),
-                        attn_alpha_smem_bytes(p.L, p.A, KB), st, p));
+    AttnFwdArgs pa = p;
+    pa.rpi = KB;
+    DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, 1>, dim3(images * KB), dim3(kAlphaThreads),
+                        attn_alpha_smem_bytes(p.L, p.A, 1), st, pa));
     DIC_LAUNCH_CHECK();
   }
   {

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
                                                             const float* __restrict__ logits,
                                                             const float* __restrict__ lse_in,
                                                             float* __restrict__ lse_out, int V, int end_id,
-                                                            float* __restrict__ cand_v, int* __restrict__ cand_i) {
+                                                            float* __restrict__ cand_v, int* __restrict__ cand_i,
+                                                            int staged) {
   __shared__ float scratch[64];
   __shared__ float wv[8];
   __shared__ int wi[8];
@@ -119,6 +120,20 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
   const int j = r % K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* lg = logits + (size_t)r * V;
+  // Stage the logits row in shared memory with 16-byte loads (one trip to L2/HBM instead of three
+  // scalar passes); rows too long for the 47 KB window are read from global memory as before.
+  extern __shared__ __align__(16) float row_s[];
+  if (staged) {
+    if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0) {
+      const float4* src4 = reinterpret_cast<const float4*>(lg);
+      float4* dst4 = reinterpret_cast<float4*>(row_s);
+      for (int i = tid; i < V / 4; i += 256) dst4[i] = __ldg(src4 + i);
+    } else {
+      for (int v = tid; v < V; v += 256) row_s[v] = lg[v];
+    }
+    __syncthreads();
+    lg = row_s;
+  }
   float ls;
   if (lse_in) {
     ls = lse_in[r];
@@ -135,51 +150,63 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
   const float sc = scores[r];
   const bool fin = finished[r] != 0;
 
-  float lv[K];
-  int li[K];
-#pragma unroll
-  for (int q = 0; q < K; ++q) { lv[q] = -INFINITY; li[q] = 0x7fffffff; }
-  for (int v = tid; v < V; v += 256) {
-    float c;
-    if (fin) c = (v == end_id) ? sc : -INFINITY;
-    else c = __fadd_rn(sc, __fsub_rn(lg[v], ls));
-    const int fi = j * V + v;
-    if (cand_better(c, fi, lv[K - 1], li[K - 1])) {
-      lv[K - 1] = c; li[K - 1] = fi;
-#pragma unroll
-      for (int q = K - 1; q > 0; --q) {
-        if (cand_better(lv[q], li[q], lv[q - 1], li[q - 1])) {
-          const float tv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = tv;
-          const int ti = li[q]; li[q] = li[q - 1]; li[q - 1] = ti;
-        }
-      }
+  // candidate values, in place in shared memory when the row is staged
+  if (staged) {
+    for (int v = tid; v < V; v += 256) {
+      float c;
+      if (fin) c = (v == end_id) ? sc : -INFINITY;
+      else c = __fadd_rn(sc, __fsub_rn(row_s[v], ls));
+      row_s[v] = c;
     }
+    __syncthreads();
   }
-  // K rounds of block-wide arg-best over the heads of the per-thread sorted lists
+  auto cand = [&](int v) -> float {
+    if (staged) return row_s[v];
+    if (fin) return (v == end_id) ? sc : -INFINITY;
+    return __fadd_rn(sc, __fsub_rn(lg[v], ls));
+  };
+  // Selection by K rounds of block arg-best.  Every thread caches the best not-yet-taken candidate
+  // of its own strided slice; only the thread that wins a round rescans its slice (the first
+  // version kept a sorted K-list per thread and was instruction bound on the insertions).
+  // Order: value descending, index ascending; a thread scans v ascending, so strict '>' keeps the
+  // lowest index among equal values.
+  float tv = INFINITY;     // last candidate taken from this thread's slice
+  int ti = -1;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  auto rescan = [&]() {
+    bv = -INFINITY;
+    bi = 0x7fffffff;
+    for (int v = tid; v < V; v += 256) {
+      const float c = cand(v);
+      const bool elig = (c < tv) || (c == tv && v > ti);
+      if (elig && (bi == 0x7fffffff || c > bv)) { bv = c; bi = v; }
+    }
+  };
+  rescan();
   for (int rd = 0; rd < K; ++rd) {
-    const int hi = li[0];
-    float bv = lv[0];
-    int bi = hi;
+    float wvv = bv;
+    int wii = bi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      const float ov = __shfl_xor_sync(0xffffffffu, wvv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wii, o);
+      if (cand_better(ov, oi, wvv, wii)) { wvv = ov; wii = oi; }
     }
-    if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+    if (lane == 0) { wv[warp] = wvv; wi[warp] = wii; }
     __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < 8; ++w)
-        if (cand_better(wv[w], wi[w], bv, bi)) { bv = wv[w]; bi = wi[w]; }
-      s_win = bi;
-      cand_v[(size_t)r * K + rd] = bv;
-      cand_i[(size_t)r * K + rd] = bi;
+        if (cand_better(wv[w], wi[w], wvv, wii)) { wvv = wv[w]; wii = wi[w]; }
+      s_win = wii;
+      cand_v[(size_t)r * K + rd] = wvv;
+      cand_i[(size_t)r * K + rd] = j * V + wii;
     }
     __syncthreads();
-    if (hi == s_win && hi != 0x7fffffff) {  // pop the winner's head (flat indices are unique)
-#pragma unroll
-      for (int q = 0; q < K - 1; ++q) { lv[q] = lv[q + 1]; li[q] = li[q + 1]; }
-      lv[K - 1] = -INFINITY; li[K - 1] = 0x7fffffff;
+    if (bi == s_win && bi != 0x7fffffff) {   // this thread's candidate was taken: find its next one
+      tv = bv;
+      ti = bi;
+      rescan();
     }
     __syncthreads();
   }
@@ -236,10 +263,11 @@ inline int launch_beam_select(const float* scores, const uint8_t* finished, cons
   if (K > V) DIC_FAIL(-4, "beam %d larger than vocabulary %d", K, V);
   float* cv = reinterpret_cast<float*>(workspace);
   int* ci = reinterpret_cast<int*>(cv + (size_t)B * K * K);
+  const int staged = (sizeof(float) * (size_t)V <= 47 * 1024) ? 1 : 0;
 #define DIC_TOPK_CASE(KK)                                                                                  \
   case KK:                                                                                                 \
-    DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK>, dim3(B * KK), dim3(256), 0, st, scores, finished, logits, \
-                        lse_in, lse_out, V, end_id, cv, ci));                                              \
+    DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK>, dim3(B * KK), dim3(256), staged ? sizeof(float) * V : 0, \
+                        st, scores, finished, logits, lse_in, lse_out, V, end_id, cv, ci, staged));        \
     DIC_LAUNCH_CHECK();                                                                                    \
     DIC_CUDA(launch_pdl(beam_merge_kernel<KK>, dim3(cdiv(B, 4)), dim3(128), 0, st, (const float*)cv,       \
                         (const int*)ci, finished, B, V, end_id, new_scores, back, tok, new_finished));     \

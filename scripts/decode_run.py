@@ -40,6 +40,7 @@ torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(reps):
     run()
+t_cpu = (time.perf_counter() - t0) / reps          # host time to enqueue (no sync inside beam/greedy for beam)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / reps
-print(f"{mode} B={B}: {dt*1e3:.3f} ms per call, {B/dt:.0f} captions/s")
+print(f"{mode} B={B}: {dt*1e3:.3f} ms per call ({t_cpu*1e3:.3f} ms host enqueue), {B/dt:.0f} captions/s")
