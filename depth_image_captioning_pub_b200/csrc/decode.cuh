@@ -264,6 +264,7 @@ inline int launch_beam_select(const float* scores, const uint8_t* finished, cons
   float* cv = reinterpret_cast<float*>(workspace);
   int* ci = reinterpret_cast<int*>(cv + (size_t)B * K * K);
   const int staged = (sizeof(float) * (size_t)V <= 47 * 1024) ? 1 : 0;
+  ProfScope prof(P_BEAM_SELECT, st, (double)B * K * V * sizeof(float));
 #define DIC_TOPK_CASE(KK)                                                                                  \
   case KK:                                                                                                 \
     DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK>, dim3(B * KK), dim3(256), staged ? sizeof(float) * V : 0, \

@@ -124,8 +124,18 @@ static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long 
   GemmArgs g = gemm_args_nt(X, is_bf16, XW, pk.Wg(), is_bf16, XW, gate_part, 0, 4 * d.H, rows, 4 * d.H,
                             (int)XW, nullptr);
   // only a handful of 128x128 output tiles exist (M = batch, N = 4H): split K across the SMs
-  int s = tc_gemm_eligible(g) ? cdiv((int)XW, kTcBK) : pick_splits(rows, 4 * d.H, (int)XW);
+  // (as many as it takes to cover the SMs about twice; large row counts need few or none)
+  int s;
+  if (tc_gemm_eligible(g)) {
+    const long long tiles = (long long)cdiv(rows, kTcBM) * cdiv(4 * d.H, 128);
+    s = (int)((2 * 148 + tiles - 1) / tiles);
+    const int kb = cdiv((int)XW, kTcBK);
+    if (s > kb) s = kb;
+  } else {
+    s = pick_splits(rows, 4 * d.H, (int)XW);
+  }
   if (s > kGateSplitsMax) s = kGateSplitsMax;
+  if (s < 1) s = 1;
   g.splits = s;
   g.split_mode = 1;
   g.split_stride = (long long)rows_alloc * 4 * d.H;

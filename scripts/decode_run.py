@@ -44,3 +44,17 @@ t_cpu = (time.perf_counter() - t0) / reps          # host time to enqueue (no sy
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / reps
 print(f"{mode} B={B}: {dt*1e3:.3f} ms per call ({t_cpu*1e3:.3f} ms host enqueue), {B/dt:.0f} captions/s")
+
+if os.environ.get("DIC_DECODE_PROFILE"):
+    from depth_image_captioning_pub_b200 import _lib
+    lib = _lib.load()
+    lib.dic_profile_enable(1)
+    run()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    lib.dic_profile_enable(0)
+    tot = sum(v[0] for v in prof.values())
+    print(f"per-class CUDA-event time of one call (no PDL while profiling), total {tot:.3f} ms:")
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        if v[1]:
+            print(f"  {k:20s} {v[0]*1e3:9.1f} us  {v[1]:4d} launches  avg {v[0]*1e3/v[1]:7.1f} us")
