@@ -9,10 +9,12 @@ The arithmetic lives in csrc/ (hand-written CUDA behind the C ABI in include/dic
 from ._lib import DicError  # noqa: F401
 from .attention import Gumbel_softmax, Hard_Attention, Soft_Attention  # noqa: F401
 from .decoders import (CD_RNNDecoderWithHardAttention, CD_RNNDecoderWithSoftAttention,  # noqa: F401
+                       MD_RNNDecoderWithHardAttention, MD_RNNDecoderWithSoftAttention,
                        RNNDecoderWithHardAttention, RNNDecoderWithSoftAttention)
 
 __all__ = [
     "DicError", "Gumbel_softmax", "Hard_Attention", "Soft_Attention",
     "CD_RNNDecoderWithHardAttention", "CD_RNNDecoderWithSoftAttention",
+    "MD_RNNDecoderWithHardAttention", "MD_RNNDecoderWithSoftAttention",
     "RNNDecoderWithHardAttention", "RNNDecoderWithSoftAttention",
 ]

@@ -278,3 +278,56 @@ class RNNDecoderWithHardAttention(_DecoderBase):
     def batch_sample(self, features: torch.Tensor, word_to_id: list, max_length=30):
         tokens, _ = self._greedy(_lib.ATTN_GUMBEL_MAX, features, None, word_to_id, max_length, False)
         return tokens.cpu().numpy().astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# depth (concat-fusion, "MD_") decoders: torch.cat((features, depth_features), dim=2) instead of the
+# add (depth_models.py:376,433,478,851,907,963,1009), then exactly the base decoder at
+# dim_encoder = mlp_dim_encoder (2048 + 32 = 2080 in config.py:19).  No reference script instantiates
+# them; they are provided for completeness.  The concatenation is a plain
+# copy done by torch (data movement, no arithmetic); everything else runs in the CUDA library.
+# ---------------------------------------------------------------------------------------------
+def _concat(features: torch.Tensor, depth_features: torch.Tensor) -> torch.Tensor:
+    if not features.is_cuda:
+        raise DicError("features must be CUDA tensors: this decoder has no CPU fallback")
+    return torch.cat((features, depth_features.to(features.dtype)), dim=2)
+
+
+class MD_RNNDecoderWithSoftAttention(RNNDecoderWithSoftAttention):
+    """depth_models.py:309-517."""
+
+    def __init__(self, dim_attention: int, dim_embedding: int, mlp_dim_encoder: int, dim_decoder: int,
+                 vocab_size: int, dropout: float = 0.5):
+        super().__init__(dim_attention, dim_embedding, mlp_dim_encoder, dim_decoder, vocab_size, dropout)
+
+    def forward(self, features, depth_features, captions, lengths):   # noqa: D102
+        return super().forward(_concat(features, depth_features), captions, lengths)
+
+    def sample(self, features, depth_features, word_to_id, max_length=30):
+        return super().sample(_concat(features, depth_features), word_to_id, max_length)
+
+    def batch_sample(self, features, depth_features, word_to_id, max_length=30):
+        return super().batch_sample(_concat(features, depth_features), word_to_id, max_length)
+
+    def beam_search(self, features, depth_features, word_to_id, beam: int = 5, max_length=30, trace=False):
+        return super().beam_search(_concat(features, depth_features), word_to_id, beam, max_length, trace)
+
+
+class MD_RNNDecoderWithHardAttention(RNNDecoderWithHardAttention):
+    """depth_models.py:792-1049."""
+
+    def __init__(self, dim_attention: int, dim_embedding: int, mlp_dim_encoder: int, dim_decoder: int,
+                 vocab_size: int, device: str, dropout: float = 0.5):
+        super().__init__(dim_attention, dim_embedding, mlp_dim_encoder, dim_decoder, vocab_size, device, dropout)
+
+    def forward(self, features, depth_features, captions, lengths, temp):   # noqa: D102
+        return super().forward(_concat(features, depth_features), captions, lengths, temp)
+
+    def eval_forward(self, features, depth_features, captions, lengths):
+        return super().eval_forward(_concat(features, depth_features), captions, lengths)
+
+    def sample(self, features, depth_features, word_to_id, max_length=30):
+        return super().sample(_concat(features, depth_features), word_to_id, max_length)
+
+    def batch_sample(self, features, depth_features, word_to_id, max_length=30):
+        return super().batch_sample(_concat(features, depth_features), word_to_id, max_length)
