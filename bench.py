@@ -171,7 +171,8 @@ def run_reference(args):
 def workload_config(n_gpus, batch):
     return {"workload": "depth-soft teacher-forced training step (fwd+loss+bwd+AdamW), BASELINE.json configs[1]",
             "batch_per_gpu": batch, "global_batch": batch * n_gpus, "decoder_steps": T, "L": L, "D": D, "A": A,
-            "E": E, "H": H, "V": V, "storage": "bf16 annotations/att1/GEMM operands, fp32 accumulate and state",
+            "E": E, "H": H, "V": V, "loss": "CE(ignore <null>) + 0.7*mean((1-sum_t alpha)^2), fused head (forward_loss)",
+            "storage": "bf16 annotations/att1/GEMM operands, fp32 accumulate and state",
             "l2_policy": "inputs larger than L2 (annotations 2 x 205 MB bf16 per GPU, workspace ~0.5 GB)",
             "parallelism": f"dp{n_gpus}"}
 
@@ -215,9 +216,12 @@ def run_b200(args):
     allreduce = FlatGradAllReduce(params) if world > 1 else None
 
     def train_step(fr, fd, cp):
-        out, alphas = m(fr, fd, cp, lengths)
-        loss = torch.nn.functional.cross_entropy(out.data, targets, ignore_index=V - 1)
-        loss = loss + LAM * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+        if args.unfused_loss:       # the reference loop's own loss expression on the returned logits
+            out, alphas = m(fr, fd, cp, lengths)
+            loss = torch.nn.functional.cross_entropy(out.data, targets, ignore_index=V - 1)
+            loss = loss + LAM * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+        else:                       # fused loss head: same loss, same gradients
+            loss = m.forward_loss(fr, fd, cp, lengths, ignore_index=V - 1, lam=LAM)
         loss.backward()
         if allreduce is not None:   # data parallel: one flat fp32 NCCL all-reduce over NVLink
             allreduce(average=True)
@@ -371,6 +375,8 @@ def main():
     ap.add_argument("--decode-batch", type=int, default=128)
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="compute the loss with torch ops on the returned logits instead of forward_loss")
     ap.add_argument("--no-beam", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -68,6 +68,11 @@ PROTOTYPES = {
                                  _P, _SZ, _P]),
     "dic_decoder_backward": (_I, [_DP, _I, _I, _P, _P, _P, _I, _P, _I, _IP, _I, _I, _P, _P, _P, _F, _P,
                                   _PP, _P, _P, _SZ, _P]),
+    "dic_decoder_backward_ex": (_I, [_DP, _I, _I, _P, _P, _P, _I, _P, _I, _IP, _I, _I, _P, _I, _P, _P, _F, _P,
+                                     _PP, _P, _P, _SZ, _P]),
+    "dic_caption_loss_workspace_bytes": (_SZ, [_I, _I]),
+    "dic_caption_loss": (_I, [_DP, _I, _P, _P, _I, _IP, _I, _I, _I, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "dic_scale_loss_grads": (_I, [_I, _P, _P, _SZ, _P, _SZ, _P]),
     "dic_decode_workspace_bytes": (_SZ, [_DP, _I, _I, _I]),
     "dic_decode_greedy": (_I, [_DP, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "dic_decode_beam": (_I, [_DP, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P,
@@ -85,6 +90,9 @@ PROTOTYPES = {
     "dic_profile_classes": (_I, []),
     "dic_profile_class_name": (C.c_char_p, [_I]),
     "dic_profile_enable": (None, [_I]),
+    "dic_set_substreams": (None, [_I]),
+    "dic_trace_start": (_I, [_P, C.c_uint]),
+    "dic_trace_stop": (_I, [C.POINTER(C.c_uint)]),
     "dic_profile_read": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
 }
 

@@ -45,6 +45,7 @@ struct AttnFwdArgs {
   int mode;
   float inv_temp;
   int rpi;              // rows (beams) per image for the alpha kernel's row -> image map (0 = KB)
+  TraceRec* trace;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -59,6 +60,7 @@ inline size_t attn_alpha_smem_bytes(int L, int A, int KB) {
 template <typename ST, int KB>
 __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  Trace trace(p.trace);
   float* w_s = reinterpret_cast<float*>(smem_raw);
   float* att2_s = w_s + p.A;                 // [KB][A]
   float* e_s = att2_s + KB * p.A;            // [KB][Lp]
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
   }
   pdl_wait();
   pdl_trigger();
+  trace.mark();
 
   for (int i = tid; i < A; i += kAlphaThreads) w_s[i] = p.w_full[i];
   for (int i = tid; i < KB * A; i += kAlphaThreads) {
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
     float* ao = p.alpha_out + (size_t)(row0 + j) * p.alpha_stride;
     for (int l = lane; l < L; l += 32) ao[l] = e[l];
   }
+  trace.end(TK_ALPHA);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,6 +223,7 @@ inline size_t attn_ctx_smem_bytes(int L, int KB) {
 template <typename ST, int KB>
 __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwdArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  Trace trace(p.trace);
   const int L = p.L, D = p.D, A = p.A;
   const int Lp = (L + 3) & ~3;
   float* al_s = reinterpret_cast<float*>(smem_raw);          // [KB][Lp]
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
   // the annotations are static; alpha and beta come from the preceding kernels of this step
   pdl_wait();
   pdl_trigger();
+  trace.mark();
 
   for (int i = tid; i < KB * L; i += kCtxThreads) {
     const int j = i / L, l = i - j * L;
@@ -345,6 +351,7 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
       store8<ST>(reinterpret_cast<ST*>(p.zg_out) + (size_t)row * p.zg_stride + d, zg);
     }
   }
+  trace.end(TK_CTX);
 }
 
 template <typename ST, int KB>
@@ -360,6 +367,7 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
     ProfScope prof(P_ATTN_ALPHA, st, (double)images * p.L * p.A * sizeof(ST));
     AttnFwdArgs pa = p;
     pa.rpi = KB;
+    pa.trace = g_trace_host;
     DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, 1>, dim3(images * KB), dim3(kAlphaThreads),
                         attn_alpha_smem_bytes(p.L, p.A, 1), st, pa));
     DIC_LAUNCH_CHECK();
@@ -368,7 +376,9 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
     // algorithmic bytes of the context pass: the annotations once per image-step
     ProfScope prof(P_ATTN_FWD, st, (double)images * p.L * (double)p.D * sizeof(ST));
     dim3 grid(cdiv(p.D, kCtxCols), images);
-    DIC_CUDA(launch_pdl(attn_context_kernel<ST, KB>, grid, dim3(kCtxThreads), attn_ctx_smem_bytes(p.L, KB), st, p));
+    AttnFwdArgs pc = p;
+    pc.trace = g_trace_host;
+    DIC_CUDA(launch_pdl(attn_context_kernel<ST, KB>, grid, dim3(kCtxThreads), attn_ctx_smem_bytes(p.L, KB), st, pc));
     DIC_LAUNCH_CHECK();
   }
   return 0;
@@ -425,6 +435,7 @@ struct AttnBwdArgs {
   int part_rows;
   int L, D, A;
   float inv_temp;
+  TraceRec* trace;
 };
 
 template <typename ST>
@@ -436,6 +447,7 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
   const bool active = d < D;
   const ST* F = reinterpret_cast<const ST*>(p.F) + (size_t)b * L * D + d;
   float* part = p.dal_part + ((size_t)chunk * p.part_rows + b) * L;
+  Trace trace(p.trace);
 
   // `pre` is warp-uniform (rg is the warp index): the blocks below contain warp shuffles
   Raw8<ST> v0[kCtxUnroll];
@@ -449,6 +461,7 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
   }
   pdl_wait();       // dzg comes from the preceding GEMM; the annotation loads above are static
   pdl_trigger();
+  trace.mark();
 
   float dz[8];
 #pragma unroll
@@ -513,6 +526,7 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
     s = warp_sum(s);
     if (lane == 0) part[l] = s;
   }
+  trace.end(TK_BWD_STREAM);
 }
 
 constexpr int kBwdSmallThreads = 256;
@@ -537,8 +551,10 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
   const int tid = threadIdx.x;
   const float* hp = p.hp + (size_t)b * (A + D);
   ST* G = reinterpret_cast<ST*>(p.G) + (size_t)b * p.g_stride;
+  Trace trace(p.trace);
   pdl_wait();
   pdl_trigger();
+  trace.mark();
 
   for (int a = tid; a < A; a += kBwdSmallThreads) {
     w_s[a] = p.w_full[a];
@@ -637,11 +653,14 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
     G[p.gcol_att2 + a] = from_f<ST>(w_s[a] * s1);
     p.dwfull_part[(size_t)b * A + a] = s2;
   }
+  trace.end(TK_BWD_SMALL);
 }
 
 template <typename ST>
-inline int launch_attn_bwd(const AttnBwdArgs& p, int rows, cudaStream_t st) {
+inline int launch_attn_bwd(const AttnBwdArgs& p_in, int rows, cudaStream_t st) {
   if (rows <= 0) return 0;
+  AttnBwdArgs p = p_in;
+  p.trace = g_trace_host;
   const int chunks = cdiv(p.D, kCtxCols);
   {
     ProfScope prof(P_ATTN_BWD, st, (double)rows * p.L * (double)p.D * sizeof(ST));

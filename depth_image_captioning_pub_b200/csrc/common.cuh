@@ -52,13 +52,13 @@ inline std::atomic<long long> g_launches{0};
 
 enum ProfClass {
   P_ATTN_FWD = 0, P_ATTN_BWD, P_DATT1, P_GEMM_TC, P_GEMM_FMA, P_LSTM, P_FUSE, P_COLSUM,
-  P_ATTN_ALPHA, P_ATTN_BWD_SMALL, P_DFEAT, P_BEAM_SELECT, P_DECODE_MISC, P_N
+  P_ATTN_ALPHA, P_ATTN_BWD_SMALL, P_DFEAT, P_BEAM_SELECT, P_DECODE_MISC, P_LOSS, P_N
 };
 inline const char* prof_class_name(int c) {
   static const char* names[P_N] = {"attn_context_fwd", "attn_stream_bwd", "datt1", "gemm_tcgen05",
                                    "gemm_fma", "lstm_pointwise", "fuse_feats", "colsum",
                                    "attn_alpha_fwd", "attn_small_bwd", "dfeat_accumulate",
-                                   "beam_select", "decode_misc"};
+                                   "beam_select", "decode_misc", "caption_loss"};
   return (c >= 0 && c < P_N) ? names[c] : "?";
 }
 struct ProfState {
@@ -310,6 +310,107 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- in-kernel timeline trace (debug; off unless dic_trace_start was called) ----------------------
+// Thread 0 of every CTA records %globaltimer at entry, after its programmatic-dependency wait and
+// at exit.  This is the only way to see the real timeline of the PDL-chained step kernels (ncu
+// serialises launches and flushes caches; CUDA events between kernels disable the overlap).
+struct TraceRec {
+  unsigned long long t0, t1, t2;
+  int kid, blk;
+};
+enum TraceKid {
+  TK_GEMM_TC = 0 /* + GemmArgs.tag * 100 */, TK_ALPHA = 1, TK_CTX, TK_LSTM_FWD, TK_LSTM_BWD, TK_BWD_STREAM,
+  TK_BWD_SMALL, TK_ARGMAX, TK_BEAM_TOPK, TK_BEAM_MERGE, TK_BEAM_REORDER, TK_GEMM_FMA, TK_MISC
+};
+inline TraceRec* g_trace_host = nullptr;      // host mirror: launch sites pass it to the kernels by value
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_cnt = 0;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct Trace {
+  unsigned long long t0 = 0, t1 = 0;
+  TraceRec* buf = nullptr;
+  // `b` comes from the kernel's argument block (constant bank): zero cost when tracing is off
+  __device__ __forceinline__ explicit Trace(TraceRec* b) {
+    if (b != nullptr && threadIdx.x == 0) {
+      buf = b;
+      t0 = gtimer();
+    }
+  }
+  __device__ __forceinline__ void mark() {
+    if (buf) t1 = gtimer();
+  }
+  __device__ __forceinline__ void end(int kid) {
+    if (buf) {
+      const unsigned int i = atomicAdd(&g_trace_cnt, 1u);
+      if (i < g_trace_cap) {
+        TraceRec r;
+        r.t0 = t0; r.t1 = t1; r.t2 = gtimer(); r.kid = kid;
+        r.blk = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+        buf[i] = r;
+      }
+    }
+  }
+};
+
+// ---- sub-batch streams -----------------------------------------------------------------------------
+// A decoder timestep is a chain of short dependent kernels around one HBM-bound pass over the
+// annotations.  Images are independent, so the time loop runs over S contiguous sub-batches on S
+// streams: while one sub-batch streams its annotations the others sit in their latency-bound
+// kernels, and the chain latency is hidden instead of serialised.  Sub-batch 0 stays on the caller's
+// stream; the others use library-owned non-blocking streams forked / joined with events (no host
+// synchronisation; the caller still sees plain stream order).
+constexpr int kMaxSub = 8;
+struct SubStreams {
+  cudaStream_t s[kMaxSub] = {nullptr};
+  cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t join_ev[kMaxSub] = {nullptr};
+  bool ready = false;
+};
+inline thread_local SubStreams g_sub;
+inline std::atomic<int> g_sub_override{0};   // dic_set_substreams: 0 = heuristic
+
+inline int sub_fork(cudaStream_t main_st, int S, cudaStream_t* out) {
+  out[0] = main_st;
+  if (S <= 1) return 0;
+  SubStreams& g = g_sub;
+  if (!g.ready) {
+    for (int i = 1; i < kMaxSub; ++i) {
+      DIC_CUDA(cudaStreamCreateWithFlags(&g.s[i], cudaStreamNonBlocking));
+      DIC_CUDA(cudaEventCreateWithFlags(&g.join_ev[i], cudaEventDisableTiming));
+    }
+    DIC_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
+    g.ready = true;
+  }
+  DIC_CUDA(cudaEventRecord(g.fork_ev, main_st));
+  for (int i = 1; i < S; ++i) {
+    out[i] = g.s[i];
+    DIC_CUDA(cudaStreamWaitEvent(g.s[i], g.fork_ev, 0));
+  }
+  return 0;
+}
+inline int sub_join(cudaStream_t main_st, int S) {
+  SubStreams& g = g_sub;
+  for (int i = 1; i < S; ++i) {
+    DIC_CUDA(cudaEventRecord(g.join_ev[i], g.s[i]));
+    DIC_CUDA(cudaStreamWaitEvent(main_st, g.join_ev[i], 0));
+  }
+  return 0;
+}
+// sub-batch boundaries: multiples of `quantum` rows, S <= kMaxSub
+inline int sub_bounds(int B, int S, int quantum, int* r0) {
+  if (S > kMaxSub) S = kMaxSub;
+  if (S < 1) S = 1;
+  int per = cdiv(cdiv(B, S), quantum) * quantum;
+  int n = 0;
+  for (int r = 0; r < B; r += per) r0[n++] = r;
+  r0[n] = B;
+  return n;
 }
 
 }  // namespace dic

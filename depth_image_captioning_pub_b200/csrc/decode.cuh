@@ -35,12 +35,14 @@ template <typename ST>
 __global__ void __launch_bounds__(256) argmax_embed_kernel(const float* __restrict__ logits, int V,
                                                            int64_t* __restrict__ tokens,
                                                            long long tok_stride, const ST* __restrict__ emb,
-                                                           int E, ST* __restrict__ Xnext, long long x_row) {
+                                                           int E, ST* __restrict__ Xnext, long long x_row, TraceRec* trace_buf) {
   __shared__ float sv[8];
   __shared__ int si[8];
   __shared__ int s_tok;
+  Trace trace(trace_buf);
   pdl_wait();
   pdl_trigger();
+  trace.mark();
   const int r = blockIdx.x;
   const float* lg = logits + (size_t)r * V;
   float best = -INFINITY;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256) argmax_embed_kernel(const float* __restri
   __syncthreads();
   const int tok = s_tok;
   for (int e = threadIdx.x; e < E; e += 256) Xnext[(size_t)r * x_row + e] = emb[(size_t)tok * E + e];
+  trace.end(TK_ARGMAX);
 }
 
 // ---- lse[r] = log sum_v exp(logits[r,v]) -------------------------------------------------------
@@ -109,13 +112,15 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
                                                             const float* __restrict__ lse_in,
                                                             float* __restrict__ lse_out, int V, int end_id,
                                                             float* __restrict__ cand_v, int* __restrict__ cand_i,
-                                                            int staged) {
+                                                            int staged, TraceRec* trace_buf) {
   __shared__ float scratch[64];
   __shared__ float wv[8];
   __shared__ int wi[8];
   __shared__ int s_win;
+  Trace trace(trace_buf);
   pdl_wait();
   pdl_trigger();
+  trace.mark();
   const int r = blockIdx.x;            // global row = b*K + j
   const int j = r % K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -210,6 +215,7 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
     }
     __syncthreads();
   }
+  trace.end(TK_BEAM_TOPK);
 }
 
 // one warp per image: merge the K sorted row lists (K*K <= 64 candidates, two per lane)
@@ -219,12 +225,14 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(const float* __restrict
                                                          const uint8_t* __restrict__ finished, int B, int V,
                                                          int end_id, float* __restrict__ new_scores,
                                                          int32_t* __restrict__ back, int32_t* __restrict__ tok,
-                                                         uint8_t* __restrict__ new_finished) {
+                                                         uint8_t* __restrict__ new_finished, TraceRec* trace_buf) {
+  Trace trace(trace_buf);
   pdl_wait();
   pdl_trigger();
+  trace.mark();
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (b >= B) return;
+  if (b >= B) { trace.end(TK_BEAM_MERGE); return; }
   constexpr int N = K * K;
   float v0 = -INFINITY, v1 = -INFINITY;
   int i0 = 0x7fffffff, i1 = 0x7fffffff;
@@ -250,6 +258,7 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(const float* __restrict
     if (i0 == bi && bi != 0x7fffffff) { v0 = -INFINITY; i0 = 0x7fffffff; }
     if (i1 == bi && bi != 0x7fffffff) { v1 = -INFINITY; i1 = 0x7fffffff; }
   }
+  trace.end(TK_BEAM_MERGE);
 }
 
 inline size_t beam_select_workspace_bytes(int B, int K) { return (size_t)B * K * K * (sizeof(float) + sizeof(int)); }
@@ -268,10 +277,11 @@ inline int launch_beam_select(const float* scores, const uint8_t* finished, cons
 #define DIC_TOPK_CASE(KK)                                                                                  \
   case KK:                                                                                                 \
     DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK>, dim3(B * KK), dim3(256), staged ? sizeof(float) * V : 0, \
-                        st, scores, finished, logits, lse_in, lse_out, V, end_id, cv, ci, staged));        \
+                        st, scores, finished, logits, lse_in, lse_out, V, end_id, cv, ci, staged, g_trace_host));         \
     DIC_LAUNCH_CHECK();                                                                                    \
     DIC_CUDA(launch_pdl(beam_merge_kernel<KK>, dim3(cdiv(B, 4)), dim3(128), 0, st, (const float*)cv,       \
-                        (const int*)ci, finished, B, V, end_id, new_scores, back, tok, new_finished));     \
+                        (const int*)ci, finished, B, V, end_id, new_scores, back, tok, new_finished,     \
+                        g_trace_host));     \
     break;
   switch (K) {
     DIC_TOPK_CASE(1) DIC_TOPK_CASE(2) DIC_TOPK_CASE(3) DIC_TOPK_CASE(4)
@@ -292,9 +302,11 @@ __global__ void __launch_bounds__(256) beam_reorder_kernel(const ST* __restrict_
                                                            const ST* __restrict__ emb,
                                                            ST* __restrict__ Xnext, long long x_row, int col_h,
                                                            float* __restrict__ c, int rows, int K, int E,
-                                                           int H) {
+                                                           int H, TraceRec* trace_buf) {
+  Trace trace(trace_buf);
   pdl_wait();
   pdl_trigger();
+  trace.mark();
   const int W = E + H;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < rows * W; i += gridDim.x * 256) {
     const int r = i / W, q = i - r * W;
@@ -307,6 +319,7 @@ __global__ void __launch_bounds__(256) beam_reorder_kernel(const ST* __restrict_
       c[(size_t)r * H + j] = c_tmp[(size_t)src * H + j];
     }
   }
+  trace.end(TK_BEAM_REORDER);
 }
 
 // ---- final backtrack from row 0 (top-k output is sorted, so row 0 is the best hypothesis) --------

@@ -6,6 +6,7 @@
 #include "gemm_generic.cuh"
 #include "gemm_tc.cuh"
 #include "layout.cuh"
+#include "loss.cuh"
 #include "lstm.cuh"
 #include "misc.cuh"
 
@@ -113,6 +114,7 @@ static int hproj(const dic_dims& d, const Pack& pk, const ST* h, long long h_ld,
                             d.A + d.D, d.H, pk.bias_db());
   g.sig_lo = d.A;
   g.sig_hi = d.A + d.D;
+  g.tag = 1;
   return gemm(g, st);
 }
 
@@ -139,8 +141,21 @@ static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long 
   g.splits = s;
   g.split_mode = 1;
   g.split_stride = (long long)rows_alloc * 4 * d.H;
+  g.tag = 2;
   *splits_out = s;
   return gemm(g, st);
+}
+
+// Number of sub-batch streams of a time loop.  Measured on B200 (scripts/sub_sweep.py, gpurun_out/sweep1.log):
+// 2 streams gain 1% on the training step and lose 10% on decode, more streams lose everywhere -- the
+// streaming kernels fill every SM's register file (8 CTAs x 64 regs x 128 threads), so another
+// stream's kernels cannot become resident next to them and only the launch count grows.  Hence 1
+// unless the caller asks (dic_set_substreams); the facility stays for shapes where it pays.
+static int pick_substreams(int images, int training) {
+  (void)images; (void)training;
+  const int o = g_sub_override.load();
+  if (o > 0 && !g_prof.on) return o;    // per-kernel event timing wants kernels timed alone
+  return 1;
 }
 
 // =============================================================================================
@@ -189,45 +204,60 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
     DIC_LAUNCH_CHECK();
   }
 
-  int off = 0;
+  // time loop: S sub-batches of images on S streams (see common.cuh, "sub-batch streams")
+  int offs[DIC_MAX_STEPS + 1];
+  offs[0] = 0;
+  for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + sizes.n[t];
+  int r0s[kMaxSub + 1];
+  const int S = sub_bounds(B, pick_substreams(B, 1), 8, r0s);
+  cudaStream_t ss[kMaxSub];
+  DIC_TRY(sub_fork(st, S, ss));
   for (int t = 0; t < T; ++t) {
-    const int n = sizes.n[t];
-    ST* X = XH + (size_t)t * B * XW;
-    ST* Xn = XH + (size_t)(t + 1) * B * XW;
-    float* HPt = HP + (size_t)t * B * (d.A + d.D);
-    DIC_TRY(hproj<ST>(d, pk, X + d.E + d.D, (long long)XW, n, HPt, st));
+    for (int sb = 0; sb < S; ++sb) {
+      const int r0 = r0s[sb];
+      const int n = (sizes.n[t] < r0s[sb + 1] ? sizes.n[t] : r0s[sb + 1]) - r0;
+      if (n <= 0) continue;
+      cudaStream_t sst = ss[sb];
+      const int off = offs[t] + r0;                       // packed row of this sub-batch's first image
+      ST* X = XH + ((size_t)t * B + r0) * XW;
+      ST* Xn = XH + ((size_t)(t + 1) * B + r0) * XW;
+      float* HPt = HP + ((size_t)t * B + r0) * (d.A + d.D);
+      DIC_TRY(hproj<ST>(d, pk, X + d.E + d.D, (long long)XW, n, HPt, sst));
 
-    AttnFwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.F = F; a.att1 = att1; a.hp = HPt; a.w_full = pk.w_full(); a.b_full = pk.b_full();
-    a.u = u ? u + (size_t)off * d.L : nullptr;
-    a.alpha_out = alphas + (size_t)t * d.L;
-    a.alpha_stride = (long long)T * d.L;
-    a.z_out = Z + (size_t)t * B * d.D;
-    a.zg_out = X + d.E;
-    a.zg_stride = (long long)XW;
-    a.L = d.L; a.D = d.D; a.A = d.A;
-    a.mode = attn_mode;
-    a.inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
-    DIC_TRY(launch_attn_step<ST>(a, n, 1, st));
+      AttnFwdArgs a;
+      memset(&a, 0, sizeof(a));
+      a.F = F + (size_t)r0 * d.L * d.D; a.att1 = att1 + (size_t)r0 * d.L * d.A; a.hp = HPt;
+      a.w_full = pk.w_full(); a.b_full = pk.b_full();
+      a.u = u ? u + (size_t)off * d.L : nullptr;
+      a.alpha_out = alphas + ((size_t)r0 * T + t) * d.L;
+      a.alpha_stride = (long long)T * d.L;
+      a.z_out = Z + ((size_t)t * B + r0) * d.D;
+      a.zg_out = X + d.E;
+      a.zg_stride = (long long)XW;
+      a.L = d.L; a.D = d.D; a.A = d.A;
+      a.mode = attn_mode;
+      a.inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
+      DIC_TRY(launch_attn_step<ST>(a, n, 1, sst));
 
-    int splits = 1;
-    DIC_TRY(gates_gemm<ST>(d, pk, X, (long long)XW, n, B, gate_part, &splits, st));
+      int splits = 1;
+      float* gp = gate_part + (size_t)r0 * 4 * d.H;
+      DIC_TRY(gates_gemm<ST>(d, pk, X, (long long)XW, n, B, gp, &splits, sst));
 
-    LstmFwdArgs l;
-    memset(&l, 0, sizeof(l));
-    l.gate_part = gate_part; l.part_stride = (long long)B * 4 * d.H; l.splits = splits;
-    l.bias_g = pk.bias_g();
-    l.c_in = c_all + (size_t)t * B * d.H;
-    l.c_out = c_all + (size_t)(t + 1) * B * d.H;
-    l.acts = acts + (size_t)t * B * 4 * d.H;
-    l.h_out = Xn + d.E + d.D; l.h_stride = (long long)XW;
-    l.hdrop_out = Hdrop + (size_t)off * d.H;
-    l.mask = dropout_mask ? dropout_mask + (size_t)off * d.H : nullptr;
-    l.rows = n; l.H = d.H;
-    DIC_TRY(launch_lstm_fwd<ST>(l, st));
-    off += n;
+      LstmFwdArgs l;
+      memset(&l, 0, sizeof(l));
+      l.gate_part = gp; l.part_stride = (long long)B * 4 * d.H; l.splits = splits;
+      l.bias_g = pk.bias_g();
+      l.c_in = c_all + ((size_t)t * B + r0) * d.H;
+      l.c_out = c_all + ((size_t)(t + 1) * B + r0) * d.H;
+      l.acts = acts + ((size_t)t * B + r0) * 4 * d.H;
+      l.h_out = Xn + d.E + d.D; l.h_stride = (long long)XW;
+      l.hdrop_out = Hdrop + (size_t)off * d.H;
+      l.mask = dropout_mask ? dropout_mask + (size_t)off * d.H : nullptr;
+      l.rows = n; l.H = d.H;
+      DIC_TRY(launch_lstm_fwd<ST>(l, sst));
+    }
   }
+  DIC_TRY(sub_join(st, S));
 
   // logits for every packed row at once: linear(dropout(h)) (depth_models.py:197), written in
   // PackedSequence (time-major) order
@@ -243,7 +273,7 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
 template <typename ST>
 static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* pack,
                                  const int64_t* captions, int cap_stride, const StepSizes& sizes,
-                                 int total, int T, int B, const float* d_logits, const float* d_alphas,
+                                 int total, int T, int B, const void* d_logits, int dl_is_st, const float* d_alphas,
                                  const float* alphas, float temp, const float* dropout_mask,
                                  const dic_params& gr, void* d_feats, int dfeat_bf16, const void* f_rgb_alias, char* ws,
                                  cudaStream_t st) {
@@ -289,9 +319,11 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   // bf16 mode: the two contractions over d_logits take a bf16 copy (tensor-core operand)
   const void* dl = d_logits;
   int dl_bf16 = 0;
-  if (is_bf16) {
+  if (is_bf16 && dl_is_st) {
+    dl_bf16 = 1;          // the fused loss head already wrote d_logits in bf16
+  } else if (is_bf16) {
     void* dl16 = ws + lay.dlogits16;
-    DIC_TRY(launch_copy2d(d_logits, V, dl16, V, 1, total, V, st));
+    DIC_TRY(launch_copy2d(reinterpret_cast<const float*>(d_logits), V, dl16, V, 1, total, V, st));
     dl = dl16;
     dl_bf16 = 1;
   }
@@ -308,63 +340,81 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   int dh_splits = cdiv((int)GW, kTcBK) / 4;      // >= 4 k-blocks of 64 per split
   if (dh_splits > kDhSplitsMax) dh_splits = kDhSplitsMax;
   if (dh_splits < 1) dh_splits = 1;
-  int off = total;
+  int offs[DIC_MAX_STEPS + 1];
+  offs[0] = 0;
+  for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + sizes.n[t];
+  int r0s[kMaxSub + 1];
+  const int S = sub_bounds(B, pick_substreams(B, 1), 8, r0s);
+  cudaStream_t ss[kMaxSub];
+  DIC_TRY(sub_fork(st, S, ss));
   for (int t = T - 1; t >= 0; --t) {
-    const int n = sizes.n[t];
-    off -= n;
-    ST* Gt = G + (size_t)t * B * GW;
-    float* HPt = HP + (size_t)t * B * (A + D);
+    for (int sb = 0; sb < S; ++sb) {
+      const int r0 = r0s[sb];
+      const int n = (sizes.n[t] < r0s[sb + 1] ? sizes.n[t] : r0s[sb + 1]) - r0;
+      if (n <= 0) continue;
+      cudaStream_t sst = ss[sb];
+      const int off = offs[t] + r0;
+      ST* Gt = G + ((size_t)t * B + r0) * GW;
+      float* HPt = HP + ((size_t)t * B + r0) * (A + D);
+      float* dhp = dh_part + (size_t)r0 * H;
+      float* dzg_s = dzg + (size_t)r0 * D;
 
-    LstmBwdArgs lb;
-    memset(&lb, 0, sizeof(lb));
-    lb.dh_carry = dh_part; lb.dh_stride = (long long)B * H; lb.dh_splits = dh_splits;
-    lb.dh_rows = (t + 1 < T) ? sizes.n[t + 1] : 0;       // rows that were active one step later
-    lb.dh_out = dHout + (size_t)off * H;
-    lb.mask = dropout_mask ? dropout_mask + (size_t)off * H : nullptr;
-    lb.dc_carry = dc;
-    lb.acts = acts + (size_t)t * B * 4 * H;
-    lb.c_new = c_all + (size_t)(t + 1) * B * H;
-    lb.c_prev = c_all + (size_t)t * B * H;
-    lb.G = Gt; lb.g_stride = GW; lb.rows = n; lb.H = H;
-    DIC_TRY(launch_lstm_bwd<ST>(lb, st));
+      LstmBwdArgs lb;
+      memset(&lb, 0, sizeof(lb));
+      lb.dh_carry = dhp; lb.dh_stride = (long long)B * H; lb.dh_splits = dh_splits;
+      // rows (of this sub-batch) that were active one step later
+      int nxt = (t + 1 < T) ? (sizes.n[t + 1] < r0s[sb + 1] ? sizes.n[t + 1] : r0s[sb + 1]) - r0 : 0;
+      lb.dh_rows = nxt > 0 ? nxt : 0;
+      lb.dh_out = dHout + (size_t)off * H;
+      lb.mask = dropout_mask ? dropout_mask + (size_t)off * H : nullptr;
+      lb.dc_carry = dc + (size_t)r0 * H;
+      lb.acts = acts + ((size_t)t * B + r0) * 4 * H;
+      lb.c_new = c_all + ((size_t)(t + 1) * B + r0) * H;
+      lb.c_prev = c_all + ((size_t)t * B + r0) * H;
+      lb.G = Gt; lb.g_stride = GW; lb.rows = n; lb.H = H;
+      DIC_TRY(launch_lstm_bwd<ST>(lb, sst));
 
-    // dzg = dgates . W_ih[:, E:E+D]
-    {
-      GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, reinterpret_cast<const ST*>(pk.Wg()) + E, is_bf16, 0, dzg,
-                                0, D, n, D, 4 * H, nullptr);
-      g.b_n = 1; g.b_k = XW;
-      DIC_TRY(gemm(g, st));     // no split-K here: a memset node would break the PDL kernel chain
-    }
+      // dzg = dgates . W_ih[:, E:E+D]
+      {
+        GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, reinterpret_cast<const ST*>(pk.Wg()) + E, is_bf16, 0, dzg_s,
+                                  0, D, n, D, 4 * H, nullptr);
+        g.b_n = 1; g.b_k = XW;
+        g.tag = 3;
+        DIC_TRY(gemm(g, sst));     // no split-K here: a memset node would break the PDL kernel chain
+      }
 
-    AttnBwdArgs ab;
-    memset(&ab, 0, sizeof(ab));
-    ab.F = F; ab.att1 = att1; ab.hp = HPt;
-    ab.z = Z + (size_t)t * B * D; ab.dzg = dzg;
-    ab.alpha = alphas + (size_t)t * L; ab.alpha_stride = (long long)T * L;
-    ab.dalpha = d_alphas ? d_alphas + (size_t)t * L : nullptr;
-    ab.w_full = pk.w_full();
-    ab.G = Gt; ab.g_stride = GW; ab.gcol_att2 = 4 * H; ab.gcol_beta = 4 * H + A;
-    ab.DZ = DZ + (size_t)t * B * D;
-    ab.de_out = de + (size_t)t * B * L;
-    ab.dwfull_part = dwfull_part + (size_t)t * B * A;
-    ab.dbfull_part = dbfull_part + (size_t)t * B;
-    ab.dal_part = reinterpret_cast<float*>(ws + lay.dal_part);
-    ab.part_rows = B;
-    ab.L = L; ab.D = D; ab.A = A; ab.inv_temp = inv_temp;
-    DIC_TRY(launch_attn_bwd<ST>(ab, n, st));
+      AttnBwdArgs ab;
+      memset(&ab, 0, sizeof(ab));
+      ab.F = F + (size_t)r0 * L * D; ab.att1 = att1 + (size_t)r0 * L * A; ab.hp = HPt;
+      ab.z = Z + ((size_t)t * B + r0) * D; ab.dzg = dzg_s;
+      ab.alpha = alphas + ((size_t)r0 * T + t) * L; ab.alpha_stride = (long long)T * L;
+      ab.dalpha = d_alphas ? d_alphas + ((size_t)r0 * T + t) * L : nullptr;
+      ab.w_full = pk.w_full();
+      ab.G = Gt; ab.g_stride = GW; ab.gcol_att2 = 4 * H; ab.gcol_beta = 4 * H + A;
+      ab.DZ = DZ + ((size_t)t * B + r0) * D;
+      ab.de_out = de + ((size_t)t * B + r0) * L;
+      ab.dwfull_part = dwfull_part + ((size_t)t * B + r0) * A;
+      ab.dbfull_part = dbfull_part + ((size_t)t * B + r0);
+      ab.dal_part = reinterpret_cast<float*>(ws + lay.dal_part) + (size_t)r0 * L;
+      ab.part_rows = B;
+      ab.L = L; ab.D = D; ab.A = A; ab.inv_temp = inv_temp;
+      DIC_TRY(launch_attn_bwd<ST>(ab, n, sst));
 
-    // dh_{t-1} = [dgates | datt2 | dbeta'] . [W_hh ; W_dec ; W_beta]
-    {
-      // K = 4H+A+D is long and the output tiny: split-K into partial buffers that the next
-      // lstm_bwd (and the final reduce) sum in a fixed order -- no memset, no atomics
-      GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, pk.Whdb(), is_bf16, 0, dh_part, 0, H, n, H, (int)GW, nullptr);
-      g.b_n = 1; g.b_k = H;
-      g.splits = dh_splits;
-      g.split_mode = 1;
-      g.split_stride = (long long)B * H;
-      DIC_TRY(gemm(g, st));
+      // dh_{t-1} = [dgates | datt2 | dbeta'] . [W_hh ; W_dec ; W_beta]
+      {
+        // K = 4H+A+D is long and the output tiny: split-K into partial buffers that the next
+        // lstm_bwd (and the final reduce) sum in a fixed order -- no memset, no atomics
+        GemmArgs g = gemm_args_nt(Gt, is_bf16, GW, pk.Whdb(), is_bf16, 0, dhp, 0, H, n, H, (int)GW, nullptr);
+        g.b_n = 1; g.b_k = H;
+        g.splits = dh_splits;
+        g.split_mode = 1;
+        g.split_stride = (long long)B * H;
+        g.tag = 4;
+        DIC_TRY(gemm(g, sst));
+      }
     }
   }
+  DIC_TRY(sub_join(st, S));
   // dh0 (rows [0, bs_valid[0]) = all B rows)
   DIC_CUDA(launch_pdl(reduce_parts_kernel, dim3(cdiv(B * H, 256)), dim3(256), 0, st, (const float*)dh_part,
                       (long long)B * H, dh_splits, dh, B * H));
@@ -503,61 +553,82 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
     DIC_LAUNCH_CHECK();
   }
 
+  // time loop over sub-batches of images on their own streams (common.cuh, "sub-batch streams"):
+  // a decode step is ~9 short dependent kernels, so the sub-batches' chains overlap almost freely
+  int i0s[kMaxSub + 1];
+  const int S = sub_bounds(B, pick_substreams(B, 0), 4, i0s);
+  cudaStream_t ss[kMaxSub];
+  DIC_TRY(sub_fork(st, S, ss));
   for (int t = 0; t < max_len; ++t) {
-    ST* X = XH + (size_t)(t & 1) * R * XW;
-    ST* Xn = XH + (size_t)((t + 1) & 1) * R * XW;
-    DIC_TRY(hproj<ST>(d, pk, X + E + D, XW, R, HP, st));
+    for (int sb = 0; sb < S; ++sb) {
+      const int i0 = i0s[sb], Bs = i0s[sb + 1] - i0;      // images of this sub-batch
+      const size_t r0 = (size_t)i0 * K;                    // first row
+      const int Rs = Bs * K;
+      cudaStream_t sst = ss[sb];
+      ST* X = XH + ((size_t)(t & 1) * R + r0) * XW;
+      ST* Xn = XH + ((size_t)((t + 1) & 1) * R + r0) * XW;
+      float* HPs = HP + r0 * (A + D);
+      DIC_TRY(hproj<ST>(d, pk, X + E + D, XW, Rs, HPs, sst));
 
-    AttnFwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.F = F; a.att1 = att1; a.hp = HP; a.w_full = pk.w_full(); a.b_full = pk.b_full();
-    a.u = u ? u + (size_t)t * R * L : nullptr;
-    a.alpha_out = alphas_out ? alphas_out + (size_t)t * R * L : reinterpret_cast<float*>(ws + lay.alpha);
-    a.alpha_stride = L;
-    a.z_out = nullptr;
-    a.zg_out = X + E; a.zg_stride = XW;
-    a.L = L; a.D = D; a.A = A; a.mode = attn_mode; a.inv_temp = 1.f;
-    DIC_TRY(launch_attn_step<ST>(a, B, K, st));
+      AttnFwdArgs a;
+      memset(&a, 0, sizeof(a));
+      a.F = F + (size_t)i0 * L * D; a.att1 = att1 + (size_t)i0 * L * A; a.hp = HPs;
+      a.w_full = pk.w_full(); a.b_full = pk.b_full();
+      a.u = u ? u + ((size_t)t * R + r0) * L : nullptr;
+      a.alpha_out = alphas_out ? alphas_out + ((size_t)t * R + r0) * L
+                               : reinterpret_cast<float*>(ws + lay.alpha) + r0 * L;
+      a.alpha_stride = L;
+      a.z_out = nullptr;
+      a.zg_out = X + E; a.zg_stride = XW;
+      a.L = L; a.D = D; a.A = A; a.mode = attn_mode; a.inv_temp = 1.f;
+      DIC_TRY(launch_attn_step<ST>(a, Bs, K, sst));
 
-    int splits = 1;
-    DIC_TRY(gates_gemm<ST>(d, pk, X, XW, R, R, gate_part, &splits, st));
+      int splits = 1;
+      float* gp = gate_part + r0 * 4 * H;
+      DIC_TRY(gates_gemm<ST>(d, pk, X, XW, Rs, R, gp, &splits, sst));
 
-    LstmFwdArgs l;
-    memset(&l, 0, sizeof(l));
-    l.gate_part = gate_part; l.part_stride = (long long)R * 4 * H; l.splits = splits;
-    l.bias_g = pk.bias_g();
-    l.c_in = c;
-    l.c_out = beam ? c_tmp : c;
-    l.h_out = beam ? h_tmp : Xn + E + D;
-    l.h_stride = beam ? H : XW;
-    l.rows = R; l.H = H;
-    DIC_TRY(launch_lstm_fwd<ST>(l, st));
+      LstmFwdArgs l;
+      memset(&l, 0, sizeof(l));
+      l.gate_part = gp; l.part_stride = (long long)R * 4 * H; l.splits = splits;
+      l.bias_g = pk.bias_g();
+      l.c_in = c + r0 * H;
+      l.c_out = beam ? c_tmp + r0 * H : c + r0 * H;
+      l.h_out = beam ? h_tmp + r0 * H : Xn + E + D;
+      l.h_stride = beam ? H : XW;
+      l.rows = Rs; l.H = H;
+      DIC_TRY(launch_lstm_fwd<ST>(l, sst));
 
-    float* lg = logits_out ? logits_out + (size_t)t * R * V : logits_ws;
-    const ST* hsrc = beam ? h_tmp : Xn + E + D;
-    GemmArgs g = gemm_args_nt(hsrc, is_bf16, beam ? H : XW, pk.Wout(), is_bf16, H, lg, 0, V, R, V, H, pk.b_out());
-    DIC_TRY(gemm(g, st));
+      float* lg = logits_out ? logits_out + ((size_t)t * R + r0) * V : logits_ws + r0 * V;
+      const ST* hsrc = beam ? h_tmp + r0 * H : Xn + E + D;
+      GemmArgs g = gemm_args_nt(hsrc, is_bf16, beam ? H : XW, pk.Wout(), is_bf16, H, lg, 0, V, Rs, V, H, pk.b_out());
+      g.tag = 5;
+      DIC_TRY(gemm(g, sst));
 
-    if (!beam) {
-      DIC_CUDA(launch_pdl(argmax_embed_kernel<ST>, dim3(R), dim3(256), 0, st, lg, V, tokens + t, (long long)max_len,
-                          reinterpret_cast<const ST*>(pk.Emb()), E, Xn, XW));
-      DIC_LAUNCH_CHECK();
-    } else {
-      float* lse_t = lse_out ? lse_out + (size_t)t * R : lse_ws;
-      int32_t* back_t = back_ws + (size_t)t * R;
-      int32_t* tok_t = tok_ws + (size_t)t * R;
-      // row log-sum-exp + per-row top-K in one kernel, then a per-image merge
-      DIC_TRY(launch_beam_select(sc[t & 1], fin[t & 1], lg, nullptr, lse_t, B, K, V, end_id, ws + lay.cand,
-                                 sc[(t + 1) & 1], back_t, tok_t, fin[(t + 1) & 1], st));
-      DIC_CUDA(launch_pdl(beam_reorder_kernel<ST>, dim3(cdiv(R * (E + H), 256)), dim3(256), 0, st, (const ST*)h_tmp,
-                          (const float*)c_tmp, (const int32_t*)back_t, (const int32_t*)tok_t,
-                          reinterpret_cast<const ST*>(pk.Emb()), Xn, XW, E + D, c, R, K, E, H));
-      DIC_LAUNCH_CHECK();
-      if (step_scores_out)
-        DIC_CUDA(cudaMemcpyAsync(step_scores_out + (size_t)t * R, sc[(t + 1) & 1], sizeof(float) * R,
-                                 cudaMemcpyDeviceToDevice, st));
+      if (!beam) {
+        DIC_CUDA(launch_pdl(argmax_embed_kernel<ST>, dim3(Rs), dim3(256), 0, sst, (const float*)lg, V,
+                            tokens + r0 * max_len + t, (long long)max_len,
+                            reinterpret_cast<const ST*>(pk.Emb()), E, Xn, XW, g_trace_host));
+        DIC_LAUNCH_CHECK();
+      } else {
+        float* lse_t = lse_out ? lse_out + (size_t)t * R + r0 : lse_ws + r0;
+        int32_t* back_t = back_ws + (size_t)t * R + r0;
+        int32_t* tok_t = tok_ws + (size_t)t * R + r0;
+        // row log-sum-exp + per-row top-K in one kernel, then a per-image merge
+        DIC_TRY(launch_beam_select(sc[t & 1] + r0, fin[t & 1] + r0, lg, nullptr, lse_t, Bs, K, V, end_id,
+                                   ws + lay.cand + r0 * K * (sizeof(float) + sizeof(int)),
+                                   sc[(t + 1) & 1] + r0, back_t, tok_t, fin[(t + 1) & 1] + r0, sst));
+        DIC_CUDA(launch_pdl(beam_reorder_kernel<ST>, dim3(cdiv(Rs * (E + H), 256)), dim3(256), 0, sst,
+                            (const ST*)(h_tmp + r0 * H), (const float*)(c_tmp + r0 * H), (const int32_t*)back_t,
+                            (const int32_t*)tok_t, reinterpret_cast<const ST*>(pk.Emb()), Xn, XW, E + D,
+                            c + r0 * H, Rs, K, E, H, g_trace_host));
+        DIC_LAUNCH_CHECK();
+        if (step_scores_out)
+          DIC_CUDA(cudaMemcpyAsync(step_scores_out + (size_t)t * R + r0, sc[(t + 1) & 1] + r0, sizeof(float) * Rs,
+                                   cudaMemcpyDeviceToDevice, sst));
+      }
     }
   }
+  DIC_TRY(sub_join(st, S));
   if (beam) {
     beam_backtrack_kernel<<<cdiv(B, 128), 128, 0, st>>>(back_ws, tok_ws, sc[max_len & 1], B, K, max_len,
                                                         end_id, tokens, lengths, scores_out);
@@ -610,6 +681,24 @@ int dic_profile_read(float* ms, long long* launches, double* bytes) {
   return 0;
 }
 const char* dic_last_error(void) { return g_err; }
+
+int dic_trace_start(void* buf, unsigned int capacity_records) {
+  TraceRec* b = reinterpret_cast<TraceRec*>(buf);
+  unsigned int zero = 0;
+  DIC_CUDA(cudaDeviceSynchronize());
+  DIC_CUDA(cudaMemcpyToSymbol(g_trace_cnt, &zero, sizeof(zero)));
+  DIC_CUDA(cudaMemcpyToSymbol(g_trace_cap, &capacity_records, sizeof(capacity_records)));
+  g_trace_host = b;
+  return 0;
+}
+int dic_trace_stop(unsigned int* count) {
+  DIC_CUDA(cudaDeviceSynchronize());
+  g_trace_host = nullptr;
+  if (count) DIC_CUDA(cudaMemcpyFromSymbol(count, g_trace_cnt, sizeof(unsigned int)));
+  return 0;
+}
+
+void dic_set_substreams(int n) { g_sub_override.store(n < 0 ? 0 : (n > kMaxSub ? kMaxSub : n)); }
 
 size_t dic_pack_bytes(const dic_dims* dims, int dtype) {
   if (check_dims(dims, dtype)) return 0;
@@ -681,12 +770,12 @@ int dic_decoder_forward(const dic_dims* dims, int dtype, int attn_mode, const vo
                                      sizes, total, T, B, u, temp, dropout_mask, logits, alphas, ws, st);
 }
 
-int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
-                         const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
-                         const int32_t* host_batch_sizes, int T, int B, const float* d_logits,
-                         const float* d_alphas, const float* alphas, float temp, const float* dropout_mask,
-                         const dic_params* grads, void* d_feats, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+int dic_decoder_backward_ex(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
+                            const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
+                            const int32_t* host_batch_sizes, int T, int B, const void* d_logits,
+                            int d_logits_dtype, const float* d_alphas, const float* alphas, float temp,
+                            const float* dropout_mask, const dic_params* grads, void* d_feats, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   DIC_TRY(check_dims(dims, dtype));
   // same aliasing rule as prologue(): no fused copy was made when there is no depth tensor and
   // the annotations already have the storage dtype
@@ -694,6 +783,9 @@ int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const v
       (f_depth == nullptr && feat_dtype == dtype) ? f_rgb : nullptr;
   if (!pack || !f_rgb || !captions || !host_batch_sizes || !d_logits || !alphas || !grads || !workspace)
     DIC_FAIL(-1, "null argument");
+  if (d_logits_dtype != DIC_F32 && d_logits_dtype != dtype)
+    DIC_FAIL(-1, "d_logits must be float32 or the storage dtype of the mode");
+  const int dl_is_st = d_logits_dtype == dtype;
   StepSizes sizes;
   int total = 0;
   DIC_TRY(make_sizes(host_batch_sizes, T, B, &sizes, &total));
@@ -703,12 +795,65 @@ int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const v
   char* ws = reinterpret_cast<char*>(workspace);
   if (dtype == DIC_BF16)
     return decoder_backward_impl<bf16>(*dims, attn_mode, pack, captions, cap_stride, sizes, total, T, B,
-                                       d_logits, d_alphas, alphas, temp, dropout_mask, *grads, d_feats,
+                                       d_logits, dl_is_st, d_alphas, alphas, temp, dropout_mask, *grads, d_feats,
                                        feat_dtype == DIC_BF16, f_alias,
                                        ws, st);
   return decoder_backward_impl<float>(*dims, attn_mode, pack, captions, cap_stride, sizes, total, T, B, d_logits,
-                                      d_alphas, alphas, temp, dropout_mask, *grads, d_feats, feat_dtype == DIC_BF16,
-                                      f_alias, ws, st);
+                                      dl_is_st, d_alphas, alphas, temp, dropout_mask, *grads, d_feats,
+                                      feat_dtype == DIC_BF16, f_alias, ws, st);
+}
+
+int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
+                         const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
+                         const int32_t* host_batch_sizes, int T, int B, const float* d_logits,
+                         const float* d_alphas, const float* alphas, float temp, const float* dropout_mask,
+                         const dic_params* grads, void* d_feats, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  // fp32 d_logits: bf16 mode makes its tensor-core operand copy, fp32 mode uses them as they are
+  return dic_decoder_backward_ex(dims, dtype, attn_mode, pack, f_rgb, f_depth, feat_dtype, captions, cap_stride,
+                                 host_batch_sizes, T, B, d_logits, DIC_F32,
+                                 d_alphas, alphas, temp, dropout_mask, grads, d_feats, workspace, workspace_bytes,
+                                 stream);
+}
+
+size_t dic_caption_loss_workspace_bytes(int N, int B) {
+  if (N <= 0 || B <= 0) return 0;
+  return loss_workspace_bytes(N, B);
+}
+
+int dic_caption_loss(const dic_dims* dims, int dtype, const float* logits, const int64_t* captions, int cap_stride,
+                     const int32_t* host_batch_sizes, int T, int B, int ignore_index, const float* alphas,
+                     float lam, float* loss, void* d_logits, float* d_alphas, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  DIC_TRY(check_dims(dims, dtype));
+  if (!logits || !captions || !host_batch_sizes || !loss || !d_logits || !workspace) DIC_FAIL(-1, "null argument");
+  StepSizes sizes;
+  int total = 0;
+  DIC_TRY(make_sizes(host_batch_sizes, T, B, &sizes, &total));
+  if (T + 1 > cap_stride) DIC_FAIL(-1, "captions has %d columns, need >= T+1 = %d", cap_stride, T + 1);
+  if (workspace_bytes < loss_workspace_bytes(total, B)) DIC_FAIL(-1, "workspace too small");
+  if (dtype == DIC_BF16 && reinterpret_cast<const void*>(logits) == d_logits)
+    DIC_FAIL(-1, "bf16 d_logits cannot alias the fp32 logits");
+  LossArgs p;
+  memset(&p, 0, sizeof(p));
+  p.logits = logits; p.captions = captions; p.cap_stride = cap_stride; p.sizes = sizes;
+  p.T = T; p.B = B; p.N = total; p.V = dims->V; p.L = dims->L; p.ignore_index = ignore_index;
+  p.alphas = alphas; p.lam = lam; p.loss = loss; p.d_logits = d_logits; p.d_alphas = d_alphas;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DIC_BF16) return launch_caption_loss<bf16>(p, workspace, st);
+  return launch_caption_loss<float>(p, workspace, st);
+}
+
+int dic_scale_loss_grads(int dtype, const float* grad_loss, void* d_logits, size_t n_logits, float* d_alphas,
+                         size_t n_alphas, void* stream) {
+  if (!grad_loss || !d_logits) DIC_FAIL(-1, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DIC_BF16)
+    loss_scale_kernel<bf16><<<592, 256, 0, st>>>(grad_loss, reinterpret_cast<bf16*>(d_logits), n_logits, d_alphas, n_alphas);
+  else
+    loss_scale_kernel<float><<<592, 256, 0, st>>>(grad_loss, reinterpret_cast<float*>(d_logits), n_logits, d_alphas, n_alphas);
+  DIC_LAUNCH_CHECK();
+  return 0;
 }
 
 size_t dic_decode_workspace_bytes(const dic_dims* dims, int dtype, int B, int beam) {

@@ -32,6 +32,7 @@ struct GemmArgs {
   float alpha;            // scales the product (not the bias)
   float bias_scale;
   int sig_lo, sig_hi;     // apply sigmoid to columns [sig_lo, sig_hi)
+  int tag;                // call-site id for the timeline trace
 };
 
 inline GemmArgs gemm_args_nt(const void* A, int a_bf16, long long lda, const void* B, int b_bf16,

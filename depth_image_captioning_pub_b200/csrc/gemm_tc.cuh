@@ -137,6 +137,8 @@ struct TcArgs {
   float alpha;
   int sig_lo, sig_hi;
   int tiles_m, tiles_n;
+  int tag;
+  TraceRec* trace;
 };
 
 template <int BN>
@@ -151,6 +153,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
   static_assert(!B_MN || BN >= 64, "MN-major B needs whole 64-wide blocks");
   extern __shared__ uint8_t smem_raw[];
+  Trace trace(p.trace);
   constexpr uint32_t A_BYTES = kTcBM * kTcBK * 2;
   constexpr uint32_t B_BYTES = BN * kTcBK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -199,6 +202,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // kernel's tail; operands and the output buffer may only be touched after it has completed.
   pdl_wait();
   pdl_trigger();
+  trace.mark();
 
   // tile index -> (split, m block, n block); n fastest so that concurrent CTAs share the A tile in L2
   auto decode = [&](int t, int& split, int& m0, int& n0, int& kb0, int& kb1) {
@@ -324,34 +328,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < COLS / 32; ++c) {
           const int nb = n0 + grp * COLS + c * 32;
           if (nb >= p.N || rows_valid <= 0) continue;      // warp-uniform
-          if (plain) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4*>(stg + lane * 36 + j) = make_uint4(r[c][j], r[c][j + 1], r[c][j + 2], r[c][j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float x[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int n = nb + j + e;
-                float t = __uint_as_float(r[c][j + e]) * p.alpha;
-                if (add_bias && n < p.N) t += p.bias[n];
-                if (n >= p.sig_lo && n < p.sig_hi) t = sigmoidf_acc(t);
-                x[e] = t;
-              }
-              *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(x[0], x[1], x[2], x[3]);
-            }
-          }
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stg + lane * 36 + j) = make_uint4(r[c][j], r[c][j + 1], r[c][j + 2], r[c][j + 3]);
           __syncwarp();
           const int n = nb + col4;
           char* crow = reinterpret_cast<char*>(p.C) + (coff + (size_t)(mrow0 + rrow) * p.ldc + n) * esz;
           const size_t rstep = (size_t)4 * p.ldc * esz;
           const bool full = vec_ok && (n + 3 < p.N);
+          // bias / activation are per COLUMN, and after the transpose a thread owns 4 fixed columns:
+          // one 16-byte bias load per chunk instead of a scalar load per element
+          float bz[4] = {0.f, 0.f, 0.f, 0.f};
+          bool sg[4] = {false, false, false, false};
+          if (!plain) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (add_bias && n + e < p.N) bz[e] = __ldg(p.bias + n + e);
+              sg[e] = (n + e >= p.sig_lo) && (n + e < p.sig_hi);
+            }
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rrow;
-            const float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + col4);
+            float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + col4);
+            if (!plain) {
+              v.x = fmaf(v.x, p.alpha, bz[0]); v.y = fmaf(v.y, p.alpha, bz[1]);
+              v.z = fmaf(v.z, p.alpha, bz[2]); v.w = fmaf(v.w, p.alpha, bz[3]);
+              if (sg[0]) v.x = sigmoidf_acc(v.x);
+              if (sg[1]) v.y = sigmoidf_acc(v.y);
+              if (sg[2]) v.z = sigmoidf_acc(v.z);
+              if (sg[3]) v.w = sigmoidf_acc(v.w);
+            }
             if (rr < rows_valid && n < p.N) {
               if (full) {
                 if (atomic) {
@@ -391,6 +398,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
+  trace.end(TK_GEMM_TC + 100 * p.tag);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -505,6 +513,8 @@ inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   p.alpha = g.alpha; p.sig_lo = g.sig_lo; p.sig_hi = g.sig_hi;
   p.tiles_m = cdiv(g.M, kTcBM);
   p.tiles_n = cdiv(g.N, BN);
+  p.tag = g.tag;
+  p.trace = g_trace_host;
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int grid = (int)(total < tc_num_sms() ? total : tc_num_sms());
   ProfScope prof(P_GEMM_TC, st);

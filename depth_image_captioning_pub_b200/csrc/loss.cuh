@@ -1,0 +1,182 @@
+// Fused caption-loss head: the training loop's
+//   loss = F.cross_entropy(packed_logits, packed_targets, ignore_index=<null>)
+//        + lam * ((1 - alphas.sum(dim=1)) ** 2).mean()           (depth_train.py:210-216)
+// and its gradients w.r.t. the logits and the attention weights, in four launches, one pass over the
+// logits.  The ATen sequence it replaces (log_softmax forward + backward, nll forward + backward, the
+// bf16 copy of d_logits for the tensor-core GEMMs, the regulariser's elementwise chain) moved ~1.2 GB
+// per step; this moves the logits once in and d_logits once out.
+#pragma once
+#include "common.cuh"
+
+namespace dic {
+
+struct LossArgs {
+  const float* logits;      // [N, V] packed (time-major) rows
+  const int64_t* captions;  // [B, cap_stride]; target of packed row (t, b) is captions[b, t+1]
+  int cap_stride;
+  StepSizes sizes;
+  int T, B, N, V, L;
+  int ignore_index;
+  const float* alphas;      // [B, T, L] or null
+  float lam;
+  float* loss;              // [1]
+  void* d_logits;           // [N, V] ST (may alias logits when ST = float)
+  float* d_alphas;          // [B, T, L] or null
+  float* nll;               // [N]   workspace
+  float* count;             // [1]   workspace: number of non-ignored targets
+  float* regsq;             // [B]   workspace
+};
+
+__device__ __forceinline__ int loss_target(const LossArgs& p, int r) {
+  int t = 0, off = 0;
+  while (t + 1 < p.T && r >= off + p.sizes.n[t]) { off += p.sizes.n[t]; ++t; }
+  const int b = r - off;
+  return (int)p.captions[(size_t)b * p.cap_stride + t + 1];
+}
+
+// number of non-ignored targets (the mean's denominator), one CTA
+__global__ void __launch_bounds__(1024) loss_count_kernel(const LossArgs p) {
+  __shared__ float scratch[64];
+  float c = 0.f;
+  for (int r = threadIdx.x; r < p.N; r += 1024) c += (loss_target(p, r) != p.ignore_index) ? 1.f : 0.f;
+  c = block_sum(c, scratch);
+  if (threadIdx.x == 0) p.count[0] = c;
+}
+
+// one CTA per packed row: row staged in shared memory with 16-byte loads, log-sum-exp, nll,
+// d_logits = (softmax - onehot) / count written in the storage dtype of the mode
+template <typename ST>
+__global__ void __launch_bounds__(256) loss_ce_row_kernel(const LossArgs p, int staged) {
+  extern __shared__ __align__(16) float row_s[];
+  __shared__ float scratch[64];
+  const int r = blockIdx.x, tid = threadIdx.x, V = p.V;
+  const float* lg = p.logits + (size_t)r * V;
+  if (staged) {
+    if ((V & 3) == 0) {
+      const float4* src4 = reinterpret_cast<const float4*>(lg);
+      float4* dst4 = reinterpret_cast<float4*>(row_s);
+      for (int i = tid; i < V / 4; i += 256) dst4[i] = src4[i];   // plain loads: the row may be overwritten below
+    } else {
+      for (int v = tid; v < V; v += 256) row_s[v] = lg[v];
+    }
+    __syncthreads();
+    lg = row_s;
+  }
+  const int tgt = loss_target(p, r);
+  const bool valid = tgt != p.ignore_index;
+  float m = -INFINITY;
+  for (int v = tid; v < V; v += 256) m = fmaxf(m, lg[v]);
+  m = block_max(m, scratch);
+  float s = 0.f;
+  for (int v = tid; v < V; v += 256) s += expf(lg[v] - m);
+  s = block_sum(s, scratch);
+  const float lse = m + logf(s);
+  if (tid == 0) p.nll[r] = valid ? (lse - lg[tgt]) : 0.f;
+  const float scale = valid ? 1.f / p.count[0] : 0.f;
+  ST* out = reinterpret_cast<ST*>(p.d_logits) + (size_t)r * V;
+  // (when d_logits aliases logits the row is staged, so the overwrite below is safe)
+  if ((V & 7) == 0) {
+    for (int v0 = tid * 8; v0 < V; v0 += 256 * 8) {
+      float g[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int v = v0 + q;
+        g[q] = (expf(lg[v] - lse) - ((v == tgt) ? 1.f : 0.f)) * scale;
+      }
+      store8<ST>(out + v0, g);
+    }
+  } else {
+    for (int v = tid; v < V; v += 256)
+      out[v] = from_f<ST>((expf(lg[v] - lse) - ((v == tgt) ? 1.f : 0.f)) * scale);
+  }
+}
+
+// doubly-stochastic regulariser, one CTA per image: S[l] = sum_t alpha[b,t,l];
+// regsq[b] = sum_l (1-S)^2 ; d_alpha[b,t,l] = -2 lam (1-S[l]) / (B L) for every t
+__global__ void __launch_bounds__(256) loss_reg_kernel(const LossArgs p) {
+  __shared__ float scratch[64];
+  const int b = blockIdx.x;
+  const float* al = p.alphas + (size_t)b * p.T * p.L;
+  const float gs = -2.f * p.lam / ((float)p.B * (float)p.L);
+  float sq = 0.f;
+  for (int l = threadIdx.x; l < p.L; l += 256) {
+    float S = 0.f;
+    for (int t = 0; t < p.T; ++t) S += al[(size_t)t * p.L + l];
+    const float d = 1.f - S;
+    sq += d * d;
+    if (p.d_alphas) {
+      const float g = gs * d;
+      for (int t = 0; t < p.T; ++t) p.d_alphas[((size_t)b * p.T + t) * p.L + l] = g;
+    }
+  }
+  sq = block_sum(sq, scratch);
+  if (threadIdx.x == 0) p.regsq[b] = sq;
+}
+
+// loss = sum(nll)/count + lam * sum(regsq)/(B L); one CTA, fixed reduction order
+__global__ void __launch_bounds__(1024) loss_final_kernel(const LossArgs p) {
+  __shared__ float scratch[64];
+  float a = 0.f;
+  for (int r = threadIdx.x; r < p.N; r += 1024) a += p.nll[r];
+  a = block_sum(a, scratch);
+  float q = 0.f;
+  if (p.alphas && p.lam != 0.f) {
+    for (int b = threadIdx.x; b < p.B; b += 1024) q += p.regsq[b];
+    q = block_sum(q, scratch);
+  }
+  if (threadIdx.x == 0) {
+    const float cnt = p.count[0];
+    float loss = cnt > 0.f ? a / cnt : nanf("");          // F.cross_entropy: all targets ignored -> nan
+    if (p.alphas && p.lam != 0.f) loss += p.lam * q / ((float)p.B * (float)p.L);
+    p.loss[0] = loss;
+  }
+}
+
+// upstream gradient of the scalar loss (read on the device: no host sync); a no-op when it is 1
+template <typename ST>
+__global__ void __launch_bounds__(256) loss_scale_kernel(const float* __restrict__ g, ST* __restrict__ dl, size_t n1,
+                                                         float* __restrict__ da, size_t n2) {
+  const float s = g[0];
+  if (s == 1.f) return;
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n1; i += stride) dl[i] = from_f<ST>(to_f<ST>(dl[i]) * s);
+  if (da)
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n2; i += stride) da[i] *= s;
+}
+
+inline size_t loss_workspace_bytes(int N, int B) {
+  return align_up(sizeof(float) * (size_t)N, 256) + 256 + align_up(sizeof(float) * (size_t)B, 256);
+}
+
+template <typename ST>
+inline int launch_caption_loss(LossArgs p, void* workspace, cudaStream_t st) {
+  char* ws = reinterpret_cast<char*>(workspace);
+  p.nll = reinterpret_cast<float*>(ws);
+  p.count = reinterpret_cast<float*>(ws + align_up(sizeof(float) * (size_t)p.N, 256));
+  p.regsq = reinterpret_cast<float*>(ws + align_up(sizeof(float) * (size_t)p.N, 256) + 256);
+  loss_count_kernel<<<1, 1024, 0, st>>>(p);
+  DIC_LAUNCH_CHECK();
+  const size_t row_bytes = sizeof(float) * (size_t)p.V;
+  const int staged = row_bytes <= 200 * 1024 ? 1 : 0;
+  if (!staged && reinterpret_cast<const void*>(p.logits) == p.d_logits)
+    DIC_FAIL(-4, "caption_loss: in-place d_logits needs V <= 51200");
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIC_CUDA(cudaFuncSetAttribute(loss_ce_row_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  {
+    ProfScope prof(P_LOSS, st, (double)p.N * p.V * (sizeof(float) + sizeof(ST)));
+    loss_ce_row_kernel<ST><<<p.N, 256, staged ? row_bytes : 0, st>>>(p, staged);
+    DIC_LAUNCH_CHECK();
+  }
+  if (p.alphas && p.lam != 0.f) {
+    loss_reg_kernel<<<p.B, 256, 0, st>>>(p);
+    DIC_LAUNCH_CHECK();
+  }
+  loss_final_kernel<<<1, 1024, 0, st>>>(p);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dic

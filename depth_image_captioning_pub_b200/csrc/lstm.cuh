@@ -21,14 +21,17 @@ struct LstmFwdArgs {
   const float* mask;       // [rows, H] or null
   float* h_f32_out;        // optional fp32 copy [rows, H] or null
   int rows, H;
+  TraceRec* trace;
 };
 
 template <typename ST>
 __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
+  Trace trace(p.trace);
   pdl_wait();
   pdl_trigger();
+  trace.mark();
   const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= p.rows * p.H) return;
+  if (idx >= p.rows * p.H) { trace.end(TK_LSTM_FWD); return; }
   const int r = idx / p.H, j = idx - r * p.H;
   const int H = p.H;
   // reduce the split-K partial tiles in a fixed order (deterministic); all loads are issued
@@ -66,11 +69,14 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
     const float m = p.mask ? p.mask[idx] : 1.f;
     reinterpret_cast<ST*>(p.hdrop_out)[idx] = from_f<ST>(h * m);
   }
+  trace.end(TK_LSTM_FWD);
 }
 
 template <typename ST>
-inline int launch_lstm_fwd(const LstmFwdArgs& p, cudaStream_t st) {
-  if (p.rows <= 0) return 0;
+inline int launch_lstm_fwd(const LstmFwdArgs& p_in, cudaStream_t st) {
+  if (p_in.rows <= 0) return 0;
+  LstmFwdArgs p = p_in;
+  p.trace = g_trace_host;
   ProfScope prof(P_LSTM, st);
   DIC_CUDA(launch_pdl(lstm_fwd_kernel<ST>, dim3(cdiv(p.rows * p.H, 256)), dim3(256), 0, st, p));
   DIC_LAUNCH_CHECK();
@@ -92,14 +98,17 @@ struct LstmBwdArgs {
   void* G;                // ST, row r at G + r*g_stride, columns [0,4H) = d(pre-activations)
   long long g_stride;
   int rows, H;
+  TraceRec* trace;
 };
 
 template <typename ST>
 __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
+  Trace trace(p.trace);
   pdl_wait();
   pdl_trigger();
+  trace.mark();
   const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= p.rows * p.H) return;
+  if (idx >= p.rows * p.H) { trace.end(TK_LSTM_BWD); return; }
   const int r = idx / p.H, j = idx - r * p.H;
   const int H = p.H;
   const float* a = p.acts + (size_t)r * 4 * H;
@@ -127,6 +136,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
   G[H + j] = from_f<ST>(d_f * fg * (1.f - fg));
   G[2 * H + j] = from_f<ST>(d_g * (1.f - gg * gg));
   G[3 * H + j] = from_f<ST>(d_o * og * (1.f - og));
+  trace.end(TK_LSTM_BWD);
 }
 
 // out[i] = sum_s parts[s][i]  (final dh0 after the time loop)
@@ -141,8 +151,10 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restri
 }
 
 template <typename ST>
-inline int launch_lstm_bwd(const LstmBwdArgs& p, cudaStream_t st) {
-  if (p.rows <= 0) return 0;
+inline int launch_lstm_bwd(const LstmBwdArgs& p_in, cudaStream_t st) {
+  if (p_in.rows <= 0) return 0;
+  LstmBwdArgs p = p_in;
+  p.trace = g_trace_host;
   ProfScope prof(P_LSTM, st);
   DIC_CUDA(launch_pdl(lstm_bwd_kernel<ST>, dim3(cdiv(p.rows * p.H, 256)), dim3(256), 0, st, p));
   DIC_LAUNCH_CHECK();

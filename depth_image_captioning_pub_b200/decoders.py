@@ -32,7 +32,7 @@ from torch.nn.utils.rnn import PackedSequence
 from . import _lib
 from ._lib import DicError, PARAM_KEYS
 from .attention import Hard_Attention, Soft_Attention
-from .engine import DecoderFunction, Engine, batch_sizes_from_lengths
+from .engine import CaptionLossFunction, DecoderFunction, Engine, batch_sizes_from_lengths
 
 DEFAULT_PRECISION = os.environ.get("DIC_PRECISION", "fp32")
 
@@ -121,6 +121,24 @@ class _DecoderBase(nn.Module):
         packed = PackedSequence(logits, torch.tensor(bsz, dtype=torch.int64))
         return packed, alphas
 
+    def _teacher_forced_loss(self, attn_mode, features, depth_features, captions, lengths, u, temp, ignore_index,
+                             lam):
+        """forward + the training loop's loss (depth_train.py:210-216) as one fused call -> 0-d loss."""
+        features, depth_features = self._check_feats(features, depth_features)
+        bsz = batch_sizes_from_lengths(lengths)
+        B = features.shape[0]
+        if len(lengths) != B or captions.shape[0] != B:
+            raise ValueError("features, captions and lengths disagree on the batch size")
+        if len(bsz) > _lib.MAX_STEPS:
+            raise ValueError(f"captions longer than {_lib.MAX_STEPS} steps are not supported")
+        captions = captions.to(device=features.device, dtype=torch.int64).contiguous()
+        eng = self._engine(features.shape[1], features.device)
+        mask = self._dropout_mask(sum(bsz), features.device)
+        if ignore_index is None:
+            ignore_index = -100          # F.cross_entropy default
+        return CaptionLossFunction.apply(eng, attn_mode, captions, bsz, int(ignore_index), float(lam), u,
+                                         float(temp), mask, features, depth_features, *self._param_list())
+
     def _draw_u(self, rows: int, L: int, device) -> torch.Tensor:
         # one draw for all steps == the reference's per-step torch.rand(bs_valid, k) calls on the
         # CPU generator concatenated (attention.py:17,40)
@@ -163,6 +181,12 @@ class CD_RNNDecoderWithSoftAttention(_DecoderBase):
         """-> (PackedSequence of logits, alphas [B, Tmax, L])   depth_models.py:153-207"""
         return self._teacher_forced(_lib.ATTN_SOFT, features, depth_features, captions, lengths, None, 1.0, True)
 
+    def forward_loss(self, features, depth_features, captions, lengths, ignore_index=None, lam: float = 0.7):
+        """Extension: forward + `F.cross_entropy(outputs.data, packed targets, ignore_index)
+        + lam * ((1 - alphas.sum(dim=1)) ** 2).mean()` (depth_train.py:210-216) fused; -> 0-d loss."""
+        return self._teacher_forced_loss(_lib.ATTN_SOFT, features, depth_features, captions, lengths, None, 1.0,
+                                         ignore_index, lam)
+
     def sample(self, features: torch.Tensor, depth_features: torch.Tensor, word_to_id: list, max_length=30):
         """-> (list[int], list[Tensor [1, L]])   depth_models.py:216-257"""
         tokens, alphas = self._greedy(_lib.ATTN_SOFT, features, depth_features, word_to_id, max_length, True)
@@ -197,6 +221,14 @@ class CD_RNNDecoderWithHardAttention(_DecoderBase):
         packed, _ = self._teacher_forced(_lib.ATTN_GUMBEL_SOFTMAX, features, depth_features, captions, lengths,
                                          u, float(temp), True)
         return packed
+
+    def forward_loss(self, features, depth_features, captions, lengths, temp, ignore_index=None):
+        """Extension: forward(temp) + cross entropy (hard attention has no regulariser,
+        depth_train.py:530-532) fused; -> 0-d loss."""
+        bsz = batch_sizes_from_lengths(lengths)
+        u = self._draw_u(sum(bsz), features.shape[1], features.device)
+        return self._teacher_forced_loss(_lib.ATTN_GUMBEL_SOFTMAX, features, depth_features, captions, lengths, u,
+                                         float(temp), ignore_index, 0.0)
 
     @torch.no_grad()
     def eval_forward(self, features: torch.Tensor, depth_features: torch.Tensor, captions: torch.Tensor,
@@ -235,6 +267,11 @@ class RNNDecoderWithSoftAttention(_DecoderBase):
     def forward(self, features: torch.Tensor, captions: torch.Tensor, lengths: list):
         return self._teacher_forced(_lib.ATTN_SOFT, features, None, captions, lengths, None, 1.0, True)
 
+    def forward_loss(self, features, captions, lengths, ignore_index=None, lam: float = 0.7):
+        """Extension: forward + the loss of base_train.py:156-162 fused; -> 0-d loss."""
+        return self._teacher_forced_loss(_lib.ATTN_SOFT, features, None, captions, lengths, None, 1.0,
+                                         ignore_index, lam)
+
     def sample(self, features: torch.Tensor, word_to_id: list, max_length=30):
         tokens, alphas = self._greedy(_lib.ATTN_SOFT, features, None, word_to_id, max_length, True)
         return tokens[0].tolist(), [alphas[t] for t in range(max_length)]
@@ -263,6 +300,12 @@ class RNNDecoderWithHardAttention(_DecoderBase):
         packed, _ = self._teacher_forced(_lib.ATTN_GUMBEL_SOFTMAX, features, None, captions, lengths, u,
                                          float(temp), True)
         return packed
+
+    def forward_loss(self, features, captions, lengths, temp, ignore_index=None):
+        bsz = batch_sizes_from_lengths(lengths)
+        u = self._draw_u(sum(bsz), features.shape[1], features.device)
+        return self._teacher_forced_loss(_lib.ATTN_GUMBEL_SOFTMAX, features, None, captions, lengths, u,
+                                         float(temp), ignore_index, 0.0)
 
     @torch.no_grad()
     def eval_forward(self, features: torch.Tensor, captions: torch.Tensor, lengths: list):
@@ -303,6 +346,9 @@ class MD_RNNDecoderWithSoftAttention(RNNDecoderWithSoftAttention):
     def forward(self, features, depth_features, captions, lengths):   # noqa: D102
         return super().forward(_concat(features, depth_features), captions, lengths)
 
+    def forward_loss(self, features, depth_features, captions, lengths, ignore_index=None, lam: float = 0.7):
+        return super().forward_loss(_concat(features, depth_features), captions, lengths, ignore_index, lam)
+
     def sample(self, features, depth_features, word_to_id, max_length=30):
         return super().sample(_concat(features, depth_features), word_to_id, max_length)
 
@@ -322,6 +368,9 @@ class MD_RNNDecoderWithHardAttention(RNNDecoderWithHardAttention):
 
     def forward(self, features, depth_features, captions, lengths, temp):   # noqa: D102
         return super().forward(_concat(features, depth_features), captions, lengths, temp)
+
+    def forward_loss(self, features, depth_features, captions, lengths, temp, ignore_index=None):
+        return super().forward_loss(_concat(features, depth_features), captions, lengths, temp, ignore_index)
 
     def eval_forward(self, features, depth_features, captions, lengths):
         return super().eval_forward(_concat(features, depth_features), captions, lengths)

@@ -115,6 +115,7 @@ class Engine:
 
     def backward(self, attn_mode: int, f_rgb, f_depth, captions, batch_sizes, d_logits, d_alphas, alphas,
                  temp, dropout_mask, ws, param_shapes, need_dfeat: bool):
+        """d_logits: float32, or the storage dtype of the mode (what the fused loss head writes)."""
         d = self.dims
         B, T = f_rgb.shape[0], len(batch_sizes)
         grads = [torch.empty(s, dtype=torch.float32, device=self.device) for s in param_shapes]
@@ -122,12 +123,42 @@ class Engine:
         gs = _params_struct(grads)
         bs = (C.c_int32 * T)(*batch_sizes)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.dic_decoder_backward(
+            _lib.check(self.lib.dic_decoder_backward_ex(
                 C.byref(d), self.dtype, attn_mode, _lib.ptr(self.pack), _lib.ptr(f_rgb), _lib.ptr(f_depth),
                 _lib.dtype_code(f_rgb), _lib.ptr(captions), captions.shape[1], bs, T, B, _lib.ptr(d_logits),
-                _lib.ptr(d_alphas), _lib.ptr(alphas), float(temp), _lib.ptr(dropout_mask), C.byref(gs),
-                _lib.ptr(d_feats), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)))
+                _lib.dtype_code(d_logits), _lib.ptr(d_alphas), _lib.ptr(alphas), float(temp),
+                _lib.ptr(dropout_mask), C.byref(gs), _lib.ptr(d_feats), _lib.ptr(ws), ws.numel(),
+                _lib.stream_ptr(self.device)))
         return grads, d_feats
+
+    def caption_loss(self, logits, captions, batch_sizes, ignore_index: int, alphas, lam: float):
+        """Fused CE + doubly-stochastic regulariser (dic_caption_loss).
+        -> (loss [1] fp32, d_logits [N,V] in the storage dtype, d_alphas [B,T,L] fp32 or None)."""
+        d = self.dims
+        B, T = captions.shape[0], len(batch_sizes)
+        N = int(sum(batch_sizes))
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        if self.dtype == _lib.DIC_BF16:
+            d_logits = torch.empty(N, d.V, dtype=torch.bfloat16, device=self.device)
+        else:
+            d_logits = logits          # fp32 mode: in place
+        use_reg = alphas is not None and lam != 0.0
+        d_alphas = torch.empty_like(alphas) if use_reg else None
+        n = self.lib.dic_caption_loss_workspace_bytes(N, B)
+        ws = self._cached(("loss", N, B), n)
+        bs = (C.c_int32 * T)(*batch_sizes)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dic_caption_loss(
+                C.byref(d), self.dtype, _lib.ptr(logits), _lib.ptr(captions), captions.shape[1], bs, T, B,
+                int(ignore_index), _lib.ptr(alphas) if use_reg else None, float(lam), _lib.ptr(loss),
+                _lib.ptr(d_logits), _lib.ptr(d_alphas), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)))
+        return loss, d_logits, d_alphas
+
+    def scale_loss_grads(self, grad_loss, d_logits, d_alphas):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dic_scale_loss_grads(
+                self.dtype, _lib.ptr(grad_loss), _lib.ptr(d_logits), d_logits.numel(), _lib.ptr(d_alphas),
+                d_alphas.numel() if d_alphas is not None else 0, _lib.stream_ptr(self.device)))
 
     def greedy(self, attn_mode: int, f_rgb, f_depth, start_id: int, max_len: int, u=None,
                want_alphas: bool = False, want_logits: bool = False):
@@ -226,3 +257,58 @@ class DecoderFunction(torch.autograd.Function):
         if ctx.has_depth and ctx.needs_input_grad[8] and d_feats is not None:
             d_dep = d_feats
         return (None, None, None, None, None, None, None, d_rgb, d_dep, *grads)
+
+
+class CaptionLossFunction(torch.autograd.Function):
+    """Teacher-forced forward + fused caption loss as ONE autograd node.
+
+    loss = CE(packed logits, packed targets, ignore_index) + lam * mean((1 - sum_t alphas)^2)
+    (depth_train.py:210-216).  The logits never reach the caller: the loss kernel turns them into
+    d_logits (storage dtype) right away, and backward feeds those to dic_decoder_backward_ex.
+    Inputs: engine, attn_mode, captions, batch_sizes, ignore_index, lam, u, temp, dropout_mask,
+    f_rgb, f_depth, *17 params.  Output: loss (0-d fp32).
+    """
+
+    @staticmethod
+    def forward(ctx, engine: Engine, attn_mode: int, captions, batch_sizes, ignore_index, lam, u, temp,
+                dropout_mask, f_rgb, f_depth, *params):
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in params) or f_rgb.requires_grad
+            or (f_depth is not None and f_depth.requires_grad))
+        engine.ensure_packed(params)
+        ws = engine.train_workspace(f_rgb.shape[0], len(batch_sizes), fresh=needs_grad)
+        logits, alphas = engine.forward(attn_mode, f_rgb, f_depth, captions, batch_sizes, u, temp,
+                                        dropout_mask, ws)
+        loss, d_logits, d_alphas = engine.caption_loss(logits, captions, batch_sizes, ignore_index,
+                                                       alphas if lam != 0.0 else None, lam)
+        ctx.engine, ctx.attn_mode, ctx.batch_sizes, ctx.temp = engine, attn_mode, list(batch_sizes), temp
+        ctx.ws = ws
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        ctx.pack_key = engine._pack_key
+        ctx.has_depth = f_depth is not None
+        ctx.has_dalpha = d_alphas is not None
+        saved = [captions, f_rgb, alphas, d_logits]
+        for opt in (f_depth, u, dropout_mask, d_alphas):
+            saved.append(opt if opt is not None else torch.empty(0, device=f_rgb.device))
+        ctx.save_for_backward(*saved)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        engine: Engine = ctx.engine
+        if engine._pack_key != ctx.pack_key:
+            raise DicError("parameters were modified between forward and backward")
+        captions, f_rgb, alphas, d_logits, f_depth, u, dropout_mask, d_alphas = ctx.saved_tensors
+        f_depth = f_depth if ctx.has_depth else None
+        dropout_mask = dropout_mask if dropout_mask.numel() else None
+        d_alphas = d_alphas if ctx.has_dalpha else None
+        g = grad_loss.detach().reshape(1).to(device=f_rgb.device, dtype=torch.float32).contiguous()
+        engine.scale_loss_grads(g, d_logits, d_alphas)        # device-side no-op when the upstream gradient is 1
+        need_dfeat = ctx.needs_input_grad[9] or ctx.needs_input_grad[10]
+        grads, d_feats = engine.backward(ctx.attn_mode, f_rgb, f_depth, captions, ctx.batch_sizes, d_logits,
+                                         d_alphas, alphas, ctx.temp, dropout_mask, ctx.ws, ctx.param_shapes,
+                                         need_dfeat)
+        ctx.ws = None
+        d_rgb = d_feats if (ctx.needs_input_grad[9] and d_feats is not None) else None
+        d_dep = d_feats if (ctx.has_depth and ctx.needs_input_grad[10] and d_feats is not None) else None
+        return (None,) * 9 + (d_rgb, d_dep, *grads)

@@ -134,6 +134,34 @@ int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const v
                          const dic_params* grads, void* d_feats, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Same as dic_decoder_backward, with d_logits in either float32 or the storage dtype of the mode
+ * (d_logits_dtype = DIC_F32 / DIC_BF16): the fused loss head below writes bf16 d_logits directly,
+ * which saves the fp32 -> bf16 operand copy of the tensor-core GEMMs. */
+int dic_decoder_backward_ex(const dic_dims* dims, int dtype, int attn_mode, const void* pack,
+                            const void* f_rgb, const void* f_depth, int feat_dtype,
+                            const int64_t* captions, int cap_stride, const int32_t* host_batch_sizes,
+                            int T, int B, const void* d_logits, int d_logits_dtype,
+                            const float* d_alphas, const float* alphas, float temp,
+                            const float* dropout_mask, const dic_params* grads, void* d_feats,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused caption-loss head ----------------------------------------------
+ * Replaces the caller-side loss of the training loop (depth_train.py:210-216 / :530-532):
+ *   loss = cross_entropy(packed logits, packed targets, ignore_index, mean over non-ignored)
+ *        + lam * mean_{b,l} (1 - sum_t alphas[b,t,l])^2       (lam = 0 / alphas NULL: CE only)
+ * and returns its gradients for an upstream gradient of 1: d_logits [N,V] in the storage dtype
+ * of the mode (fp32 mode: may alias `logits`), d_alphas [B,T,L] fp32 (may be NULL).
+ * Targets are read from `captions` (target of packed row (t,b) = captions[b,t+1]).
+ * loss: [1] fp32 on the device.  No host synchronisation. */
+size_t dic_caption_loss_workspace_bytes(int N, int B);
+int dic_caption_loss(const dic_dims* dims, int dtype, const float* logits, const int64_t* captions,
+                     int cap_stride, const int32_t* host_batch_sizes, int T, int B,
+                     int ignore_index, const float* alphas, float lam, float* loss, void* d_logits,
+                     float* d_alphas, void* workspace, size_t workspace_bytes, void* stream);
+/* d_logits, d_alphas *= grad_loss[0] (device scalar); a no-op kernel when it is exactly 1. */
+int dic_scale_loss_grads(int dtype, const float* grad_loss, void* d_logits, size_t n_logits,
+                         float* d_alphas, size_t n_alphas, void* stream);
+
 /* ---- decoding -----------------------------------------------------------------------
  * dic_decode_greedy replaces .sample / .batch_sample (depth_models.py:216-305, 698-789):
  * fixed max_len steps, no early stop, next token = argmax (ties -> lowest id); no host
@@ -195,6 +223,18 @@ int dic_profile_classes(void);
 const char* dic_profile_class_name(int cls);
 void dic_profile_enable(int on);
 int dic_profile_read(float* ms, long long* launches, double* bytes);
+
+/* Number of image sub-batches (each on its own library-owned stream, forked from and joined back
+ * into the caller's stream with events) the time loops of forward / backward / decode run over.
+ * 0 (default) = chosen from the batch size; 1 = everything on the caller's stream. */
+void dic_set_substreams(int n);
+
+/* Debug timeline: while a trace is active, thread 0 of every CTA of the step kernels appends a
+ * 32-byte record {u64 t_entry, t_after_dependency_wait, t_exit (globaltimer ns); i32 kernel id,
+ * linear block id} to buf (device memory, capacity_records records).  Both calls synchronise the
+ * device.  dic_trace_stop returns the number of records produced (may exceed the capacity). */
+int dic_trace_start(void* buf, unsigned int capacity_records);
+int dic_trace_stop(unsigned int* count);
 
 /* GEMM test hook: C[M,N] (fp32) = A[M,K] . B[N,K]^T (+bias[N]); a_dtype/b_dtype storage.
  * engine 0 = CUDA-core FMA path, 1 = tcgen05/TMA path (bf16 operands, K % 64 == 0).
