@@ -38,6 +38,8 @@ struct AttnFwdArgs {
   const float* u;       // [rows, L] uniform draws or null
   float* alpha_out;     // row r at alpha_out + r*alpha_stride (required: (a) -> (b) hand-off)
   long long alpha_stride;
+  bf16* alpha16_out;    // optional bf16 copy (A operand of the fused dL/dF GEMM), row r at + r*alpha16_stride
+  long long alpha16_stride;
   float* z_out;         // [rows, D] fp32 or null (saved for backward)
   void* zg_out;         // ST, row r at zg_out + r*zg_stride
   long long zg_stride;
@@ -208,6 +210,10 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
     }
     float* ao = p.alpha_out + (size_t)(row0 + j) * p.alpha_stride;
     for (int l = lane; l < L; l += 32) ao[l] = e[l];
+    if (p.alpha16_out) {
+      bf16* a16 = p.alpha16_out + (size_t)(row0 + j) * p.alpha16_stride;
+      for (int l = lane; l < L; l += 32) a16[l] = __float2bfloat16_rn(e[l]);
+    }
   }
   trace.end(TK_ALPHA);
 }

@@ -3,6 +3,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "decode.cuh"
+#include "dfeat_tc.cuh"
 #include "gemm_generic.cuh"
 #include "gemm_tc.cuh"
 #include "layout.cuh"
@@ -186,6 +187,8 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
   // invalid (b >= bs_valid) rows of the step buffers must stay finite zeros: the post-loop
   // weight-gradient GEMMs run over all T*B rows.
   DIC_CUDA(cudaMemsetAsync(XH, 0, ((size_t)T * B + B) * XW * sizeof(ST), st));
+  bf16* alpha16 = is_bf16 ? reinterpret_cast<bf16*>(ws + lay.alpha16) : nullptr;
+  if (alpha16) DIC_CUDA(cudaMemsetAsync(alpha16, 0, (size_t)T * B * lay.Lp * 2, st));
 
   const ST* F = nullptr;
   DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, att1, &F, st));
@@ -231,6 +234,8 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
       a.u = u ? u + (size_t)off * d.L : nullptr;
       a.alpha_out = alphas + ((size_t)r0 * T + t) * d.L;
       a.alpha_stride = (long long)T * d.L;
+      a.alpha16_out = alpha16 ? alpha16 + ((size_t)r0 * T + t) * lay.Lp : nullptr;
+      a.alpha16_stride = (long long)T * lay.Lp;
       a.z_out = Z + ((size_t)t * B + r0) * d.D;
       a.zg_out = X + d.E;
       a.zg_stride = (long long)XW;
@@ -495,7 +500,13 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 
   // dL/dF = datt1 . W_enc + sum_t alpha_t (x) dz_t + dmeanF / L
   // (written in the annotations' dtype: fp32 in place, bf16 through the fp32 accumulation buffer dF32)
-  if (d_feats) {
+  if (d_feats && is_bf16 && dfeat_bf16 && dfeat_tc_eligible(A, D, lay.Lp)) {
+    // one tensor-core GEMM over K = A + T, bf16 dF written once (dfeat_tc.cuh)
+    DIC_TRY(launch_dfeat_tc(reinterpret_cast<const bf16*>(datt1), reinterpret_cast<const bf16*>(pk.Wenc()),
+                            reinterpret_cast<const bf16*>(ws + lay.alpha16), lay.Lp,
+                            reinterpret_cast<const bf16*>(DZ), dmeanF, reinterpret_cast<bf16*>(d_feats), B, L, D, A,
+                            T, st));
+  } else if (d_feats) {
     float* acc = dfeat_bf16 ? reinterpret_cast<float*>(ws + lay.dF32) : reinterpret_cast<float*>(d_feats);
     GemmArgs g = gemm_args_nt(datt1, is_bf16, A, pk.Wenc(), is_bf16, 0, acc, 0, D, B * L, D, A, nullptr);
     g.b_n = 1; g.b_k = D;
@@ -1030,6 +1041,15 @@ int dic_row_lse(const float* logits, int R, int V, float* lse, void* stream) {
   row_lse_kernel<<<R, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, V, lse);
   DIC_LAUNCH_CHECK();
   return 0;
+}
+
+int dic_dfeat_gemm(const void* datt1, const void* w_enc, const void* alpha16, int Lp, const void* dz,
+                   const float* dmeanF, void* dF, int B, int L, int D, int A, int T, void* stream) {
+  if (!datt1 || !w_enc || !alpha16 || !dz || !dmeanF || !dF) DIC_FAIL(-1, "null argument");
+  if (!dfeat_tc_eligible(A, D, Lp)) DIC_FAIL(-5, "shape not eligible for the fused dL/dF GEMM");
+  return launch_dfeat_tc(reinterpret_cast<const bf16*>(datt1), reinterpret_cast<const bf16*>(w_enc),
+                         reinterpret_cast<const bf16*>(alpha16), Lp, reinterpret_cast<const bf16*>(dz), dmeanF,
+                         reinterpret_cast<bf16*>(dF), B, L, D, A, T, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dic_gemm_nt(int engine, int M, int N, int K, const void* A, int a_dtype, const void* B, int b_dtype,

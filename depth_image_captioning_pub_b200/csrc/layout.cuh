@@ -76,6 +76,8 @@ constexpr int kDhSplitsMax = 10;     // split-K partial buffers of the per-step 
 struct TrainLayout {
   size_t Fsum, meanF, att1, XH, HP, Z, acts, c_all, gate_part, Hdrop;
   size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16, dal_part, h0, dF32, dh_part;
+  size_t alpha16;
+  int Lp;
   size_t bytes;
   size_t XW, GW;
   int es;
@@ -113,6 +115,8 @@ struct TrainLayout {
     h0 = c.take(sizeof(float) * B * d.H);
     dh_part = c.take(sizeof(float) * kDhSplitsMax * B * d.H);
     dF32 = c.take(sizeof(float) * (size_t)B * d.L * d.D);   // fp32 dL/dF accumulator when annotations are bf16
+    Lp = (d.L + 7) & ~7;
+    alpha16 = c.take(TB * Lp * 2);     // bf16 alpha [B,T,Lp]: A operand of the fused dL/dF GEMM
     bytes = c.off;
   }
 };

@@ -236,6 +236,13 @@ void dic_set_substreams(int n);
 int dic_trace_start(void* buf, unsigned int capacity_records);
 int dic_trace_stop(unsigned int* count);
 
+/* Test hook of the fused dL/dF GEMM (bf16 mode, csrc/dfeat_tc.cuh):
+ *   dF[b] (L x D, bf16) = datt1[b] (L x A) . w_enc (A x D) + alpha16[b]^T (L x T) . dz[b] (T x D) + dmeanF[b] / L
+ * datt1 [B*L, A] bf16; w_enc [A, D] bf16; alpha16 [B*T, Lp] bf16 (Lp % 8 == 0, columns >= L zero);
+ * dz [T, B, D] bf16; dmeanF [B, D] fp32. */
+int dic_dfeat_gemm(const void* datt1, const void* w_enc, const void* alpha16, int Lp, const void* dz,
+                   const float* dmeanF, void* dF, int B, int L, int D, int A, int T, void* stream);
+
 /* GEMM test hook: C[M,N] (fp32) = A[M,K] . B[N,K]^T (+bias[N]); a_dtype/b_dtype storage.
  * engine 0 = CUDA-core FMA path, 1 = tcgen05/TMA path (bf16 operands, K % 64 == 0).
  * workspace: dic_gemm_workspace_bytes (tensor maps / split-K partials). */
