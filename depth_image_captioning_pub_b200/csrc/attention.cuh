@@ -692,7 +692,7 @@ inline int launch_attn_bwd(const AttnBwdArgs& p_in, int rows, cudaStream_t st) {
 // Post-loop: datt1[b,l,a] = w[a] * sum_t de_t[b,l] 1[att1[b,l,a] + att2_t[b,a] > 0]
 // (the relu output is recomputed from att1 + att2 instead of being saved per step: saving it
 // would cost B*L*A*4 bytes per step, SURVEY.md section 7 hard part 9).
-// Grid (L chunks of 32 rows, B); 256 threads = 2 row groups x 128 columns.
+// Grid (L chunks of 32 rows, B).
 // ------------------------------------------------------------------------------------------
 struct Datt1Args {
   const void* att1;     // [B,L,A] ST
@@ -704,40 +704,72 @@ struct Datt1Args {
   StepSizes sizes;
 };
 
+// CTA = 32 annotation rows x 128 columns of one image, 128 threads; a thread owns 8 rows x 4 columns.
+// att2_t and de_t tiles are staged in shared memory (32 steps at a time), so the inner loop is three
+// 16-byte shared loads per step for 32 mask-and-add updates.  (The first version read de_t[l] and
+// att2_t[a] from global memory per update and took 107 us for 13 MB of traffic.)
+constexpr int kDatt1TT = 32;
 template <typename ST>
-__global__ void __launch_bounds__(256) datt1_kernel(const Datt1Args p) {
-  constexpr int RPT = 16;  // rows per thread
+__global__ void __launch_bounds__(128) datt1_kernel(const Datt1Args p) {
+  __shared__ __align__(16) float a2_s[kDatt1TT][128];
+  __shared__ __align__(16) float de_s[kDatt1TT][32];
   const int b = blockIdx.y;
-  const int l0 = blockIdx.x * (2 * RPT);
-  const int rg = threadIdx.x >> 7, a0 = threadIdx.x & 127;
+  const int l0 = blockIdx.x * 32;
+  const int tid = threadIdx.x, cg = tid & 31, rq = tid >> 5;
   int Tb = 0;
   for (int t = 0; t < p.T; ++t) Tb += (p.sizes.n[t] > b) ? 1 : 0;
   const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)b * p.L * p.A;
   ST* out = reinterpret_cast<ST*>(p.datt1) + (size_t)b * p.L * p.A;
   for (int ab = 0; ab < p.A; ab += 128) {
-    const int a = ab + a0;
-    if (a >= p.A) continue;
-    float v[RPT], acc[RPT];
+    const int a = ab + cg * 4;
+    const bool col_ok = a < p.A;            // A % 4 == 0: a thread's 4 columns are in or out together
+    float v[8][4], acc[8][4];
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int l = l0 + rg + 2 * r;
-      v[r] = l < p.L ? to_f<ST>(att1[(size_t)l * p.A + a]) : 0.f;
-      acc[r] = 0.f;
+    for (int r = 0; r < 8; ++r) {
+      const int l = l0 + rq * 8 + r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { v[r][q] = 0.f; acc[r][q] = 0.f; }
+      if (col_ok && l < p.L) load4<ST>(att1 + (size_t)l * p.A + a, v[r]);
     }
-    for (int t = 0; t < Tb; ++t) {
-      const float a2 = p.hp_all[((size_t)t * p.B + b) * (p.A + p.D) + a];
-      const float* de = p.de_all + ((size_t)t * p.B + b) * p.L;
+    for (int t0 = 0; t0 < Tb; t0 += kDatt1TT) {
+      const int tn = min(kDatt1TT, Tb - t0);
+      __syncthreads();
+      for (int i = tid; i < tn * 128; i += 128) {
+        const int t = i >> 7, c = i & 127;
+        a2_s[t][c] = (ab + c < p.A) ? p.hp_all[((size_t)(t0 + t) * p.B + b) * (p.A + p.D) + ab + c] : 0.f;
+      }
+      for (int i = tid; i < tn * 32; i += 128) {
+        const int t = i >> 5, r = i & 31;
+        de_s[t][r] = (l0 + r < p.L) ? p.de_all[((size_t)(t0 + t) * p.B + b) * p.L + l0 + r] : 0.f;
+      }
+      __syncthreads();
+      for (int t = 0; t < tn; ++t) {
+        const float4 a2 = *reinterpret_cast<const float4*>(&a2_s[t][cg * 4]);
+        const float4 d0 = *reinterpret_cast<const float4*>(&de_s[t][rq * 8]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&de_s[t][rq * 8 + 4]);
+        const float de[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const float a2v[4] = {a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        const int l = l0 + rg + 2 * r;
-        if (l < p.L && v[r] + a2 > 0.f) acc[r] += de[l];
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (v[r][q] + a2v[q] > 0.f) acc[r][q] += de[r];
       }
     }
-    const float w = p.w_full[a];
+    if (col_ok) {
+      float w[4];
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int l = l0 + rg + 2 * r;
-      if (l < p.L) out[(size_t)l * p.A + a] = from_f<ST>(w * acc[r]);
+      for (int q = 0; q < 4; ++q) w[q] = p.w_full[a + q];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int l = l0 + rq * 8 + r;
+        if (l < p.L) {
+          float o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = w[q] * acc[r][q];
+          store4<ST>(out + (size_t)l * p.A + a, o);
+        }
+      }
     }
   }
 }
@@ -746,7 +778,7 @@ template <typename ST>
 inline int launch_datt1(const Datt1Args& p, cudaStream_t st) {
   dim3 grid(cdiv(p.L, 32), p.B);
   ProfScope prof(P_DATT1, st, (double)p.B * p.L * p.A * sizeof(ST) * 2);
-  datt1_kernel<ST><<<grid, 256, 0, st>>>(p);
+  datt1_kernel<ST><<<grid, 128, 0, st>>>(p);
   DIC_LAUNCH_CHECK();
   return 0;
 }

@@ -9,7 +9,7 @@ namespace dic {
 // ---- initial state: replicate (h0,c0) over the rows of each image, embed <start> ---------------
 template <typename ST>
 __global__ void __launch_bounds__(256) decode_init_kernel(const float* __restrict__ h0,
-                                                          const float* __restrict__ c0,
+                                                          const float* __restrict__ c0, int hc_stride,
                                                           const ST* __restrict__ emb, int start_id,
                                                           ST* __restrict__ X, long long x_row, int col_h,
                                                           float* __restrict__ c, int rows, int KB, int E,
@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(256) decode_init_kernel(const float* __restric
       X[(size_t)r * x_row + q] = emb[(size_t)start_id * E + q];
     } else {
       const int j = q - E;
-      X[(size_t)r * x_row + col_h + j] = from_f<ST>(h0[(size_t)b * H + j]);
-      c[(size_t)r * H + j] = c0[(size_t)b * H + j];
+      X[(size_t)r * x_row + col_h + j] = from_f<ST>(h0[(size_t)b * hc_stride + j]);
+      c[(size_t)r * H + j] = c0[(size_t)b * hc_stride + j];
     }
   }
 }

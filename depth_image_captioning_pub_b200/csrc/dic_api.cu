@@ -75,12 +75,12 @@ static int gemm_splitk(GemmArgs g, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <typename ST>
 static int prologue(const dic_dims& d, const Pack& pk, const void* f_rgb, const void* f_depth,
-                    int feat_dtype, int B, ST* Fsum, float* meanF, ST* att1, const ST** Fuse,
+                    int feat_dtype, int B, ST* Fsum, float* meanF, bf16* mean16, ST* att1, const ST** Fuse,
                     cudaStream_t st) {
   const int is_bf16 = sizeof(ST) == 2;
   const bool alias = (f_depth == nullptr) && ((feat_dtype == DIC_BF16) == (is_bf16 != 0));
   // base decoders with matching storage: no copy, only the mean (base_caption_models.py:118)
-  DIC_TRY(launch_fuse_feats<ST>(f_rgb, f_depth, feat_dtype == DIC_BF16, alias ? nullptr : Fsum, meanF, B,
+  DIC_TRY(launch_fuse_feats<ST>(f_rgb, f_depth, feat_dtype == DIC_BF16, alias ? nullptr : Fsum, meanF, mean16, B,
                                 d.L, d.D, st));
   const ST* F = alias ? reinterpret_cast<const ST*>(f_rgb) : Fsum;
   *Fuse = F;
@@ -103,6 +103,13 @@ static int init_state_gemm(const dic_dims& d, const Pack& pk, const float* meanF
   g = gemm_args_nt(meanF, 0, d.D, w2, is_bf16, d.D, c0, 0, d.H, B, d.H, d.D, pk.b_init() + d.H);
   DIC_TRY(gemm_splitk(g, st));
   return 0;
+}
+
+// bf16 mode: [h0 | c0] in ONE tensor-core GEMM (split-K) from the bf16 copy of mean_l F
+static int init_state_gemm_tc(const dic_dims& d, const Pack& pk, const bf16* mean16, int B, float* hc0,
+                              cudaStream_t st) {
+  GemmArgs g = gemm_args_nt(mean16, 1, d.D, pk.Winit(), 1, d.D, hc0, 0, 2 * d.H, B, 2 * d.H, d.D, pk.b_init());
+  return gemm_splitk(g, st);
 }
 
 // h-projection of a step: [att2 | beta] = [h W_dec^T + b_dec | sigmoid(h W_beta^T + b_beta)]
@@ -191,8 +198,14 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
   if (alpha16) DIC_CUDA(cudaMemsetAsync(alpha16, 0, (size_t)T * B * lay.Lp * 2, st));
 
   const ST* F = nullptr;
-  DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, att1, &F, st));
-  {
+  bf16* mean16 = is_bf16 ? reinterpret_cast<bf16*>(ws + lay.meanF16) : nullptr;
+  DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, mean16, att1, &F, st));
+  if (is_bf16) {
+    float* hc0 = reinterpret_cast<float*>(ws + lay.hc0);
+    DIC_TRY(init_state_gemm_tc(d, pk, mean16, B, hc0, st));
+    DIC_TRY(launch_copy2d(hc0, 2 * d.H, XH + d.E + d.D, (long long)XW, 1, B, d.H, st));
+    DIC_TRY(launch_copy2d(hc0 + d.H, 2 * d.H, c_all, d.H, 0, B, d.H, st));
+  } else {
     float* h0 = reinterpret_cast<float*>(ws + lay.h0);
     DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, h0, c_all, st));
     DIC_TRY(launch_copy2d(h0, d.H, XH + d.E + d.D, (long long)XW, is_bf16, B, d.H, st));
@@ -427,17 +440,35 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 
   // ---- post-loop: everything that is a sum over (t, b) is one contraction over T*B rows ----
   // init_linear: rows [0,H) from dh0, rows [H,2H) from dc0
-  for (int half = 0; half < 2; ++half) {
-    const float* dsrc = half == 0 ? dh : dc;
-    GemmArgs g = gemm_args_nt(dsrc, 0, 0, meanF, 0, 0, gr.init_w + (size_t)half * H * D, 0, D, H, D, B, nullptr);
-    g.a_m = 1; g.a_k = H; g.b_n = 1; g.b_k = D;
-    DIC_TRY(gemm_generic(g, st));
-    DIC_TRY(launch_colsum(dsrc, 0, B, H, H, gr.init_b + half * H, st));
+  if (is_bf16) {
+    // bf16 operands [dh0|dc0] and mean_l F -> two tensor-core GEMMs; the bias gradient rides on the cast
+    bf16* dhc16 = reinterpret_cast<bf16*>(ws + lay.dhc16);
+    const bf16* mean16 = reinterpret_cast<const bf16*>(ws + lay.meanF16);
+    dhc_prep_kernel<<<cdiv(2 * H, 32), 256, 0, st>>>(dh, dc, dhc16, gr.init_b, B, H);
+    DIC_LAUNCH_CHECK();
+    {
+      GemmArgs g = gemm_args_nt(dhc16, 1, 0, mean16, 1, 0, gr.init_w, 0, D, 2 * H, D, B, nullptr);
+      g.a_m = 1; g.a_k = 2 * H; g.b_n = 1; g.b_k = D;
+      DIC_TRY(gemm_splitk(g, st));
+    }
     if (d_feats) {
-      GemmArgs m = gemm_args_nt(dsrc, 0, H, reinterpret_cast<const ST*>(pk.Winit()) + (size_t)half * H * D,
-                                is_bf16, 0, dmeanF, 0, D, B, D, H, nullptr);
-      m.b_n = 1; m.b_k = D; m.accumulate = half;
-      DIC_TRY(gemm_generic(m, st));
+      GemmArgs m = gemm_args_nt(dhc16, 1, 2 * H, pk.Winit(), 1, 0, dmeanF, 0, D, B, D, 2 * H, nullptr);
+      m.b_n = 1; m.b_k = D;
+      DIC_TRY(gemm(m, st));
+    }
+  } else {
+    for (int half = 0; half < 2; ++half) {
+      const float* dsrc = half == 0 ? dh : dc;
+      GemmArgs g = gemm_args_nt(dsrc, 0, 0, meanF, 0, 0, gr.init_w + (size_t)half * H * D, 0, D, H, D, B, nullptr);
+      g.a_m = 1; g.a_k = H; g.b_n = 1; g.b_k = D;
+      DIC_TRY(gemm_generic(g, st));
+      DIC_TRY(launch_colsum(dsrc, 0, B, H, H, gr.init_b + half * H, st));
+      if (d_feats) {
+        GemmArgs m = gemm_args_nt(dsrc, 0, H, reinterpret_cast<const ST*>(pk.Winit()) + (size_t)half * H * D,
+                                  is_bf16, 0, dmeanF, 0, D, B, D, H, nullptr);
+        m.b_n = 1; m.b_k = D; m.accumulate = half;
+        DIC_TRY(gemm_generic(m, st));
+      }
     }
   }
 
@@ -553,11 +584,19 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
   int32_t* tok_ws = reinterpret_cast<int32_t*>(ws + lay.tok);
 
   const ST* F = nullptr;
-  DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, att1, &F, st));
-  DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, h0, c0, st));
+  bf16* mean16 = is_bf16 ? reinterpret_cast<bf16*>(ws + lay.meanF16) : nullptr;
+  DIC_TRY(prologue<ST>(d, pk, f_rgb, f_depth, feat_dtype, B, Fsum, meanF, mean16, att1, &F, st));
+  int hc_stride = H;
+  if (is_bf16) {
+    float* hc0 = reinterpret_cast<float*>(ws + lay.hc0);
+    DIC_TRY(init_state_gemm_tc(d, pk, mean16, B, hc0, st));
+    h0 = hc0; c0 = hc0 + H; hc_stride = 2 * H;
+  } else {
+    DIC_TRY(init_state_gemm<ST>(d, pk, meanF, B, h0, c0, st));
+  }
   DIC_CUDA(cudaMemsetAsync(XH, 0, (size_t)2 * R * XW * sizeof(ST), st));
   decode_init_kernel<ST><<<cdiv(R * (E + H), 256), 256, 0, st>>>(
-      h0, c0, reinterpret_cast<const ST*>(pk.Emb()), start_id, XH, XW, E + D, c, R, K, E, H);
+      h0, c0, hc_stride, reinterpret_cast<const ST*>(pk.Emb()), start_id, XH, XW, E + D, c, R, K, E, H);
   DIC_LAUNCH_CHECK();
   if (beam) {
     beam_state_init_kernel<<<cdiv(R, 256), 256, 0, st>>>(sc[0], fin[0], B, K);

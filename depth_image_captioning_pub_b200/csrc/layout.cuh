@@ -76,7 +76,7 @@ constexpr int kDhSplitsMax = 10;     // split-K partial buffers of the per-step 
 struct TrainLayout {
   size_t Fsum, meanF, att1, XH, HP, Z, acts, c_all, gate_part, Hdrop;
   size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16, dal_part, h0, dF32, dh_part;
-  size_t alpha16;
+  size_t alpha16, meanF16, hc0, dhc16;
   int Lp;
   size_t bytes;
   size_t XW, GW;
@@ -117,6 +117,9 @@ struct TrainLayout {
     dF32 = c.take(sizeof(float) * (size_t)B * d.L * d.D);   // fp32 dL/dF accumulator when annotations are bf16
     Lp = (d.L + 7) & ~7;
     alpha16 = c.take(TB * Lp * 2);     // bf16 alpha [B,T,Lp]: A operand of the fused dL/dF GEMM
+    meanF16 = c.take((size_t)B * d.D * 2);
+    hc0 = c.take(sizeof(float) * B * 2 * d.H);
+    dhc16 = c.take((size_t)B * 2 * d.H * 2);
     bytes = c.off;
   }
 };
@@ -124,7 +127,7 @@ struct TrainLayout {
 // Decode workspace: R = B*beam rows.
 struct DecodeLayout {
   size_t Fsum, meanF, att1, XH, HP, c, c_tmp, h_tmp, h0, c0, gate_part, logits, lse;
-  size_t scores, scores2, fin, fin2, back, tok, step_scores, alpha, cand;
+  size_t scores, scores2, fin, fin2, back, tok, step_scores, alpha, cand, meanF16, hc0;
   size_t bytes;
   size_t XW;
   int es;
@@ -155,6 +158,8 @@ struct DecodeLayout {
     step_scores = c_.take(sizeof(float) * R * max_len);
     alpha = c_.take(sizeof(float) * R * d.L);
     cand = c_.take(R * beam * (sizeof(float) + sizeof(int)));     // per-row top-K candidates
+    meanF16 = c_.take((size_t)B * d.D * 2);
+    hc0 = c_.take(sizeof(float) * B * 2 * d.H);
     bytes = c_.off;
   }
 };

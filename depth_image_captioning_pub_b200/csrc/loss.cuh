@@ -51,19 +51,55 @@ __global__ void __launch_bounds__(256) loss_ce_row_kernel(const LossArgs p, int 
   __shared__ float scratch[64];
   const int r = blockIdx.x, tid = threadIdx.x, V = p.V;
   const float* lg = p.logits + (size_t)r * V;
+  const int tgt = loss_target(p, r);
+  const bool valid = tgt != p.ignore_index;
+  ST* out = reinterpret_cast<ST*>(p.d_logits) + (size_t)r * V;
   if (staged) {
+    // one trip to global memory: the row is staged with 16-byte loads while the running max is taken;
+    // exp(x - max) is computed once and kept in shared memory for the gradient pass
+    float m = -INFINITY;
     if ((V & 3) == 0) {
       const float4* src4 = reinterpret_cast<const float4*>(lg);
       float4* dst4 = reinterpret_cast<float4*>(row_s);
-      for (int i = tid; i < V / 4; i += 256) dst4[i] = src4[i];   // plain loads: the row may be overwritten below
+      for (int i = tid; i < V / 4; i += 256) {
+        const float4 x = src4[i];            // plain loads: the row may be overwritten below (in-place d_logits)
+        dst4[i] = x;
+        m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+      }
     } else {
-      for (int v = tid; v < V; v += 256) row_s[v] = lg[v];
+      for (int v = tid; v < V; v += 256) {
+        const float x = lg[v];
+        row_s[v] = x;
+        m = fmaxf(m, x);
+      }
     }
-    __syncthreads();
-    lg = row_s;
+    m = block_max(m, scratch);               // its barriers also publish row_s
+    const float x_tgt = valid ? row_s[tgt] : 0.f;
+    __syncthreads();                         // everyone has read x_tgt before row_s is overwritten
+    float s = 0.f;
+    for (int v = tid; v < V; v += 256) {
+      const float e = expf(row_s[v] - m);
+      row_s[v] = e;
+      s += e;
+    }
+    s = block_sum(s, scratch);
+    if (tid == 0) p.nll[r] = valid ? (m + logf(s) - x_tgt) : 0.f;
+    const float scale = valid ? 1.f / p.count[0] : 0.f;
+    const float ps = scale / s;              // softmax * scale = e * ps
+    if ((V & 7) == 0) {
+      for (int v0 = tid * 8; v0 < V; v0 += 256 * 8) {
+        const float4 e0 = *reinterpret_cast<const float4*>(row_s + v0);
+        const float4 e1 = *reinterpret_cast<const float4*>(row_s + v0 + 4);
+        float g[8] = {e0.x * ps, e0.y * ps, e0.z * ps, e0.w * ps, e1.x * ps, e1.y * ps, e1.z * ps, e1.w * ps};
+        if (tgt >= v0 && tgt < v0 + 8) g[tgt - v0] -= scale;
+        store8<ST>(out + v0, g);
+      }
+    } else {
+      for (int v = tid; v < V; v += 256) out[v] = from_f<ST>(row_s[v] * ps - ((v == tgt) ? scale : 0.f));
+    }
+    return;
   }
-  const int tgt = loss_target(p, r);
-  const bool valid = tgt != p.ignore_index;
+  // rows too long for shared memory: three passes over global memory
   float m = -INFINITY;
   for (int v = tid; v < V; v += 256) m = fmaxf(m, lg[v]);
   m = block_max(m, scratch);
@@ -73,22 +109,8 @@ __global__ void __launch_bounds__(256) loss_ce_row_kernel(const LossArgs p, int 
   const float lse = m + logf(s);
   if (tid == 0) p.nll[r] = valid ? (lse - lg[tgt]) : 0.f;
   const float scale = valid ? 1.f / p.count[0] : 0.f;
-  ST* out = reinterpret_cast<ST*>(p.d_logits) + (size_t)r * V;
-  // (when d_logits aliases logits the row is staged, so the overwrite below is safe)
-  if ((V & 7) == 0) {
-    for (int v0 = tid * 8; v0 < V; v0 += 256 * 8) {
-      float g[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int v = v0 + q;
-        g[q] = (expf(lg[v] - lse) - ((v == tgt) ? 1.f : 0.f)) * scale;
-      }
-      store8<ST>(out + v0, g);
-    }
-  } else {
-    for (int v = tid; v < V; v += 256)
-      out[v] = from_f<ST>((expf(lg[v] - lse) - ((v == tgt) ? 1.f : 0.f)) * scale);
-  }
+  for (int v = tid; v < V; v += 256)
+    out[v] = from_f<ST>((expf(lg[v] - lse) - ((v == tgt) ? 1.f : 0.f)) * scale);
 }
 
 // doubly-stochastic regulariser, one CTA per image: S[l] = sum_t alpha[b,t,l];

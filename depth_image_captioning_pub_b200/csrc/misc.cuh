@@ -10,7 +10,8 @@ namespace dic {
 template <typename TIN, typename ST>
 __global__ void __launch_bounds__(256) fuse_feats_kernel(const TIN* __restrict__ rgb,
                                                          const TIN* __restrict__ dep, ST* __restrict__ fsum,
-                                                         float* __restrict__ meanF, int L, int D) {
+                                                         float* __restrict__ meanF, bf16* __restrict__ mean16,
+                                                         int L, int D) {
   const int b = blockIdx.y;
   const int d = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (d >= D) return;
@@ -56,20 +57,27 @@ __global__ void __launch_bounds__(256) fuse_feats_kernel(const TIN* __restrict__
   const float inv = 1.f / (float)L;
   *reinterpret_cast<float4*>(meanF + (size_t)b * D + d) =
       make_float4(s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv);
+  if (mean16) {     // bf16 copy: A operand of the init_linear tensor-core GEMMs
+    uint2 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+    h[0] = __floats2bfloat162_rn(s[0] * inv, s[1] * inv);
+    h[1] = __floats2bfloat162_rn(s[2] * inv, s[3] * inv);
+    *reinterpret_cast<uint2*>(mean16 + (size_t)b * D + d) = r;
+  }
 }
 
 // fsum == nullptr -> only the mean is produced (the caller aliases Fsum to the input).
 template <typename ST>
 inline int launch_fuse_feats(const void* rgb, const void* dep, int feat_bf16, ST* fsum, float* meanF,
-                             int B, int L, int D, cudaStream_t st) {
+                             bf16* mean16, int B, int L, int D, cudaStream_t st) {
   dim3 grid(cdiv(D, 1024), B);
   ProfScope prof(P_FUSE, st);
   if (feat_bf16)
     fuse_feats_kernel<bf16, ST><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(rgb),
-                                                     reinterpret_cast<const bf16*>(dep), fsum, meanF, L, D);
+                                                     reinterpret_cast<const bf16*>(dep), fsum, meanF, mean16, L, D);
   else
     fuse_feats_kernel<float, ST><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(rgb),
-                                                      reinterpret_cast<const float*>(dep), fsum, meanF, L, D);
+                                                      reinterpret_cast<const float*>(dep), fsum, meanF, mean16, L, D);
   DIC_LAUNCH_CHECK();
   return 0;
 }
@@ -106,11 +114,68 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ sr
   }
 }
 
+// wide bf16 matrices (d_logits [N,V], G [T*B, 4H+A+D]): a thread owns 8 consecutive columns (16-byte
+// loads, a warp covers 512 contiguous bytes of a row), 8 row groups per CTA, 4 rows in flight per thread
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restrict__ src, int R, int C, long long ld,
+                                                            int rows_per_block, float* __restrict__ dst) {
+  __shared__ float red[8][32][9];
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float s[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s[q] = 0.f;
+  if (c < C) {
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {
+      Raw8<bf16> raw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) raw[i].load_stream(src + (size_t)(r + 8 * i) * ld + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v[8];
+        raw[i].unpack(v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[q] += v[q];
+      }
+    }
+    for (; r < r1; r += 8) {
+      float v[8];
+      load8_stream<bf16>(src + (size_t)r * ld + c, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] += v[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) red[ry][lane][q] = s[q];
+  __syncthreads();
+  // 256 threads = 256 columns of the CTA
+  const int cl = threadIdx.x, ln = cl >> 3, q = cl & 7;
+  const int cc = blockIdx.x * 256 + cl;
+  if (cc < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][ln][q];
+    atomicAdd(dst + cc, t);
+  }
+}
+
 inline int launch_colsum(const void* src, int src_bf16, int R, int C, long long ld, float* dst,
                          cudaStream_t st) {
   ProfScope prof(P_COLSUM, st);
   DIC_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * C, st));
   if (R <= 0 || C <= 0) return 0;
+  if (src_bf16 && C >= 256 && C % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int ctiles = cdiv(C, 256);
+    int chunks = cdiv(148 * 8, ctiles);                 // ~8 CTAs per SM
+    if (chunks > cdiv(R, 32)) chunks = cdiv(R, 32);
+    if (chunks < 1) chunks = 1;
+    const int rpb = cdiv(cdiv(R, chunks), 8) * 8;
+    dim3 grid(ctiles, cdiv(R, rpb));
+    colsum_bf16x8_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(src), R, C, ld, rpb, dst);
+    DIC_LAUNCH_CHECK();
+    return 0;
+  }
   int chunks = cdiv(R, 256);
   if (chunks > 1024) chunks = 1024;
   const int rpb = cdiv(R, chunks);
@@ -197,6 +262,33 @@ inline int launch_copy2d(const float* src, long long src_ld, void* dst, long lon
 __global__ void __launch_bounds__(256) add_vec_kernel(const float* a, const float* b, float* dst, int n) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < n) dst[i] = a[i] + b[i];
+}
+
+// ---- backward of init_linear, operand prep: dhc16[b, 0:H] = dh0, [H:2H] = dc0 (bf16), and the bias
+// gradient (column sums over the batch) in the same pass.  Grid 2H/32 CTAs of 256 threads (32 columns x 8
+// row groups).
+__global__ void __launch_bounds__(256) dhc_prep_kernel(const float* __restrict__ dh, const float* __restrict__ dc,
+                                                       bf16* __restrict__ dhc16, float* __restrict__ db, int B, int H) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;          // column in [0, 2H)
+  float s = 0.f;
+  if (c < 2 * H) {
+    const float* src = c < H ? dh + c : dc + (c - H);
+    for (int r = ry; r < B; r += 8) {
+      const float v = src[(size_t)r * H];
+      s += v;
+      dhc16[(size_t)r * 2 * H + c] = __float2bfloat16_rn(v);
+    }
+  }
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < 2 * H) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    db[c] = t;
+  }
 }
 
 // ---- dL/dF accumulation -------------------------------------------------------------------------
