@@ -221,35 +221,57 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
 // ---------------------------------------------------------------------------------------------
 // (b) context: the streaming pass over the annotations
 // ---------------------------------------------------------------------------------------------
+// columns per thread / rows in flight of the context kernel: one beam per image streams with 16-byte
+// loads; with several beams the accumulators (KB x CPT registers) decide the occupancy, and 8 columns
+// per thread left 5 CTAs per SM = 1.4 waves of the 1024-CTA grid (32 us at 128 images x 5 beams against
+// 15 us with one beam).  4 columns per thread, twice the rows in flight, keeps 8 CTAs resident.
+__host__ __device__ constexpr int ctx_cpt(int KB) { return KB <= 2 ? 8 : 4; }
+__host__ __device__ constexpr int ctx_unroll(int KB) { return KB <= 2 ? kCtxUnroll : (KB <= 5 ? 12 : 8); }
+
 inline size_t attn_ctx_smem_bytes(int L, int KB) {
   const size_t Lp = (size_t)(L + 3) & ~(size_t)3;
-  return sizeof(float) * ((size_t)KB * Lp + (size_t)(kCtxGroups - 1) * KB * kCtxCols) + 32;
+  return sizeof(float) * ((size_t)KB * Lp + (size_t)(kCtxGroups - 1) * KB * 32 * ctx_cpt(KB)) + 32;
+}
+
+// acc[0..N) += al * v[0..N) as packed fp32x2 FMAs (sm_100 FFMA2; same rounding as fmaf per element).
+// With several beams per image the pass is instruction-issue bound, not HBM bound: 5 beams x 8 columns
+// = 40 scalar FMAs per 16-byte load.
+template <int N>
+__device__ __forceinline__ void ctx_fmaN(float al, const float (&v)[N], float (&acc)[N]) {
+  const float2 a2 = make_float2(al, al);
+#pragma unroll
+  for (int q = 0; q < N; q += 2) {
+    const float2 r = __ffma2_rn(a2, make_float2(v[q], v[q + 1]), make_float2(acc[q], acc[q + 1]));
+    acc[q] = r.x;
+    acc[q + 1] = r.y;
+  }
 }
 
 template <typename ST, int KB>
 __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwdArgs p) {
+  constexpr int CPT = ctx_cpt(KB), U = ctx_unroll(KB), COLS = 32 * CPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Trace trace(p.trace);
   const int L = p.L, D = p.D, A = p.A;
   const int Lp = (L + 3) & ~3;
   float* al_s = reinterpret_cast<float*>(smem_raw);          // [KB][Lp]
-  float* part_s = al_s + KB * Lp;                            // [3][KB][256]
-  int* pos_s = reinterpret_cast<int*>(part_s + (kCtxGroups - 1) * KB * kCtxCols);
+  float* part_s = al_s + KB * Lp;                            // [3][KB][COLS]
+  int* pos_s = reinterpret_cast<int*>(part_s + (kCtxGroups - 1) * KB * COLS);
 
   const int img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
   const int row0 = img * KB;
-  const int d = blockIdx.x * kCtxCols + lane * 8;
+  const int d = blockIdx.x * COLS + lane * CPT;
   const bool active = d < D;
   const ST* F = reinterpret_cast<const ST*>(p.F) + (size_t)img * L * D + d;
 
   // first batch of annotation rows goes in flight before anything else is touched
-  Raw8<ST> v0[kCtxUnroll];
+  RawV<ST, CPT> v0[U];
   const bool gmax = p.mode == DIC_ATTN_GUMBEL_MAX;
-  const bool pre = active && !gmax && (rg + (kCtxUnroll - 1) * kCtxGroups < L);
+  const bool pre = active && !gmax && (rg + (U - 1) * kCtxGroups < L);
   if (pre) {
 #pragma unroll
-    for (int r = 0; r < kCtxUnroll; ++r) v0[r].load_stream(F + (size_t)(rg + r * kCtxGroups) * D);
+    for (int r = 0; r < U; ++r) v0[r].load_stream(F + (size_t)(rg + r * kCtxGroups) * D);
   }
   // the annotations are static; alpha and beta come from the preceding kernels of this step
   pdl_wait();
@@ -264,65 +286,50 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
   }
   __syncthreads();
 
-  float acc[KB][8];
+  float acc[KB][CPT];
 #pragma unroll
   for (int j = 0; j < KB; ++j)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[j][q] = 0.f;
+    for (int q = 0; q < CPT; ++q) acc[j][q] = 0.f;
 
   if (active) {
     if (gmax) {
       // one-hot alpha: the weighted sum is a single-row gather
       if (rg == 0) {
 #pragma unroll
-        for (int j = 0; j < KB; ++j) {
-          float v[8];
-          load8<ST>(F + (size_t)pos_s[j] * D, v);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[j][q] = v[q];
-        }
+        for (int j = 0; j < KB; ++j) vloadN<ST, CPT>(F + (size_t)pos_s[j] * D, acc[j]);
       }
     } else {
       int l = rg;
       if (pre) {
 #pragma unroll
-        for (int r = 0; r < kCtxUnroll; ++r) {
-          float v[8];
+        for (int r = 0; r < U; ++r) {
+          float v[CPT];
           v0[r].unpack(v);
 #pragma unroll
-          for (int j = 0; j < KB; ++j) {
-            const float al = al_s[j * Lp + l + r * kCtxGroups];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[j][q] = fmaf(al, v[q], acc[j][q]);
-          }
+          for (int j = 0; j < KB; ++j) ctx_fmaN<CPT>(al_s[j * Lp + l + r * kCtxGroups], v, acc[j]);
         }
-        l += kCtxUnroll * kCtxGroups;
+        l += U * kCtxGroups;
       }
-      for (; l + (kCtxUnroll - 1) * kCtxGroups < L; l += kCtxUnroll * kCtxGroups) {
-        Raw8<ST> raw[kCtxUnroll];
+      for (; l + (U - 1) * kCtxGroups < L; l += U * kCtxGroups) {
+        RawV<ST, CPT> raw[U];
 #pragma unroll
-        for (int r = 0; r < kCtxUnroll; ++r) raw[r].load_stream(F + (size_t)(l + r * kCtxGroups) * D);
+        for (int r = 0; r < U; ++r) raw[r].load_stream(F + (size_t)(l + r * kCtxGroups) * D);
 #pragma unroll
-        for (int r = 0; r < kCtxUnroll; ++r) {
-          float v[8];
+        for (int r = 0; r < U; ++r) {
+          float v[CPT];
           raw[r].unpack(v);
 #pragma unroll
-          for (int j = 0; j < KB; ++j) {
-            const float al = al_s[j * Lp + l + r * kCtxGroups];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[j][q] = fmaf(al, v[q], acc[j][q]);
-          }
+          for (int j = 0; j < KB; ++j) ctx_fmaN<CPT>(al_s[j * Lp + l + r * kCtxGroups], v, acc[j]);
         }
       }
       for (; l < L; l += kCtxGroups) {
-        float v[8];
-        load8_stream<ST>(F + (size_t)l * D, v);
+        RawV<ST, CPT> raw;
+        raw.load_stream(F + (size_t)l * D);
+        float v[CPT];
+        raw.unpack(v);
 #pragma unroll
-        for (int j = 0; j < KB; ++j) {
-          const float al = al_s[j * Lp + l];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[j][q] = fmaf(al, v[q], acc[j][q]);
-        }
+        for (int j = 0; j < KB; ++j) ctx_fmaN<CPT>(al_s[j * Lp + l], v, acc[j]);
       }
     }
   }
@@ -330,9 +337,10 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
   if (rg > 0) {
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
-      float* dst = part_s + ((size_t)(rg - 1) * KB + j) * kCtxCols + lane * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+      float* dst = part_s + ((size_t)(rg - 1) * KB + j) * COLS + lane * CPT;
+#pragma unroll
+      for (int q = 0; q < CPT; q += 4)
+        *reinterpret_cast<float4*>(dst + q) = make_float4(acc[j][q], acc[j][q + 1], acc[j][q + 2], acc[j][q + 3]);
     }
   }
   __syncthreads();
@@ -341,20 +349,21 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
     for (int j = 0; j < KB; ++j) {
 #pragma unroll
       for (int g = 0; g < kCtxGroups - 1; ++g) {
-        const float* src = part_s + ((size_t)g * KB + j) * kCtxCols + lane * 8;
-        const float4 a = *reinterpret_cast<const float4*>(src);
-        const float4 b = *reinterpret_cast<const float4*>(src + 4);
-        acc[j][0] += a.x; acc[j][1] += a.y; acc[j][2] += a.z; acc[j][3] += a.w;
-        acc[j][4] += b.x; acc[j][5] += b.y; acc[j][6] += b.z; acc[j][7] += b.w;
+        const float* src = part_s + ((size_t)g * KB + j) * COLS + lane * CPT;
+#pragma unroll
+        for (int q = 0; q < CPT; q += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(src + q);
+          acc[j][q] += a.x; acc[j][q + 1] += a.y; acc[j][q + 2] += a.z; acc[j][q + 3] += a.w;
+        }
       }
       const int row = row0 + j;
-      if (p.z_out) store8<float>(p.z_out + (size_t)row * D + d, acc[j]);
-      float beta[8];
-      load8<float>(p.hp + (size_t)row * (A + D) + A + d, beta);
-      float zg[8];
+      if (p.z_out) vstoreN<float, CPT>(p.z_out + (size_t)row * D + d, acc[j]);
+      float beta[CPT];
+      vloadN<float, CPT>(p.hp + (size_t)row * (A + D) + A + d, beta);
+      float zg[CPT];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) zg[q] = beta[q] * acc[j][q];
-      store8<ST>(reinterpret_cast<ST*>(p.zg_out) + (size_t)row * p.zg_stride + d, zg);
+      for (int q = 0; q < CPT; ++q) zg[q] = beta[q] * acc[j][q];
+      vstoreN<ST, CPT>(reinterpret_cast<ST*>(p.zg_out) + (size_t)row * p.zg_stride + d, zg);
     }
   }
   trace.end(TK_CTX);
@@ -381,7 +390,7 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
   {
     // algorithmic bytes of the context pass: the annotations once per image-step
     ProfScope prof(P_ATTN_FWD, st, (double)images * p.L * (double)p.D * sizeof(ST));
-    dim3 grid(cdiv(p.D, kCtxCols), images);
+    dim3 grid(cdiv(p.D, 32 * ctx_cpt(KB)), images);
     AttnFwdArgs pc = p;
     pc.trace = g_trace_host;
     DIC_CUDA(launch_pdl(attn_context_kernel<ST, KB>, grid, dim3(kCtxThreads), attn_ctx_smem_bytes(p.L, KB), st, pc));

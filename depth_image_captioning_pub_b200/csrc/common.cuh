@@ -198,6 +198,11 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+template <typename T, int N>
+__device__ __forceinline__ void vloadN(const T* p, float (&v)[N]) {
+  if constexpr (N == 8) load8<T>(p, v); else load4<T>(p, v);
+}
+
 // Raw (unconverted) 8-element vectors: streaming kernels keep several of these in flight per
 // thread; holding bf16 data packed (4 registers instead of 8) is what lets 8+ CTAs fit per SM.
 template <typename T>
@@ -236,6 +241,35 @@ struct Raw8<float> {
   }
 };
 
+// N-element (8 or 4) raw vectors with streaming loads: RawV<T, 8> = Raw8<T>; RawV<T, 4> is half of it
+template <typename T, int N>
+struct RawV;
+template <typename T>
+struct RawV<T, 8> : Raw8<T> {};
+template <>
+struct RawV<bf16, 4> {
+  uint2 r;
+  __device__ __forceinline__ void load_stream(const bf16* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  }
+  __device__ __forceinline__ void zero() { r = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void unpack(float (&v)[4]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+    const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+  }
+};
+template <>
+struct RawV<float, 4> {
+  float4 a;
+  __device__ __forceinline__ void load_stream(const float* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+  }
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float (&v)[4]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+};
+
 template <typename T>
 __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
 template <>
@@ -250,6 +284,11 @@ __device__ __forceinline__ void store8<bf16>(bf16* p, const float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = r;
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void vstoreN(T* p, const float (&v)[N]) {
+  if constexpr (N == 8) store8<T>(p, v); else store4<T>(p, v);
 }
 
 // ---- reductions ---------------------------------------------------------------------------
@@ -363,28 +402,33 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 struct Trace {
-  unsigned long long t0 = 0, t1 = 0;
-  TraceRec* buf = nullptr;
+  TraceRec* rec = nullptr;     // this CTA's record (thread 0 only, when tracing is on): the only live state
   // `b` comes from the kernel's argument block (constant bank): zero cost when tracing is off
   __device__ __forceinline__ explicit Trace(TraceRec* b) {
+#ifndef DIC_NO_TRACE
     if (b != nullptr && threadIdx.x == 0) {
-      buf = b;
-      t0 = gtimer();
-    }
-  }
-  __device__ __forceinline__ void mark() {
-    if (buf) t1 = gtimer();
-  }
-  __device__ __forceinline__ void end(int kid) {
-    if (buf) {
       const unsigned int i = atomicAdd(&g_trace_cnt, 1u);
       if (i < g_trace_cap) {
-        TraceRec r;
-        r.t0 = t0; r.t1 = t1; r.t2 = gtimer(); r.kid = kid;
-        r.blk = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
-        buf[i] = r;
+        rec = b + i;
+        rec->t1 = 0;
+        rec->t0 = gtimer();
       }
     }
+#endif
+  }
+  __device__ __forceinline__ void mark() {
+#ifndef DIC_NO_TRACE
+    if (rec) rec->t1 = gtimer();
+#endif
+  }
+  __device__ __forceinline__ void end(int kid) {
+#ifndef DIC_NO_TRACE
+    if (rec) {
+      rec->kid = kid;
+      rec->blk = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+      rec->t2 = gtimer();
+    }
+#endif
   }
 };
 

@@ -105,7 +105,11 @@ __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) {
   return v > bv || (v == bv && i < bi);
 }
 
-template <int K>
+template <bool FAST>
+__device__ __forceinline__ float exp_sel(float x) { return FAST ? __expf(x) : expf(x); }
+
+// FAST (bf16 mode): ex2.approx-based exponentials in the row log-sum-exp; the fp32 parity mode keeps expf.
+template <int K, bool FAST>
 __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restrict__ scores,
                                                             const uint8_t* __restrict__ finished,
                                                             const float* __restrict__ logits,
@@ -125,45 +129,105 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
   const int j = r % K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* lg = logits + (size_t)r * V;
-  // Stage the logits row in shared memory with 16-byte loads (one trip to L2/HBM instead of three
-  // scalar passes); rows too long for the 47 KB window are read from global memory as before.
+  // Stage the logits row in shared memory with 16-byte loads, four in flight per thread, and take the
+  // row's log-sum-exp on the way in (online max / sum per thread, one block reduction of the pairs);
+  // rows too long for the 47 KB window are read from global memory.
   extern __shared__ __align__(16) float row_s[];
-  if (staged) {
+  float ls;
+  if (staged && !lse_in) {
+    float m = -INFINITY, ssum = 0.f;
+    // online max / sum in batches: one rescale per batch of up to 16 values, no per-element branch
+    auto push4 = [&](const float4* x, int n) {
+      float bm = m;
+      for (int u = 0; u < n; ++u) bm = fmaxf(fmaxf(bm, fmaxf(x[u].x, x[u].y)), fmaxf(x[u].z, x[u].w));
+      if (bm > m) { ssum *= exp_sel<FAST>(m - bm); m = bm; }          // exp(-inf) = 0 on the first batch
+      for (int u = 0; u < n; ++u)
+        ssum += (exp_sel<FAST>(x[u].x - m) + exp_sel<FAST>(x[u].y - m)) + (exp_sel<FAST>(x[u].z - m) + exp_sel<FAST>(x[u].w - m));
+    };
     if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0) {
       const float4* src4 = reinterpret_cast<const float4*>(lg);
       float4* dst4 = reinterpret_cast<float4*>(row_s);
-      for (int i = tid; i < V / 4; i += 256) dst4[i] = __ldg(src4 + i);
+      const int n4 = V / 4;
+      int i = tid;
+      for (; i + 3 * 256 < n4; i += 4 * 256) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = __ldg(src4 + i + u * 256);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst4[i + u * 256] = x[u];
+        push4(x, 4);
+      }
+      for (; i < n4; i += 256) {
+        const float4 x = __ldg(src4 + i);
+        dst4[i] = x;
+        push4(&x, 1);
+      }
     } else {
-      for (int v = tid; v < V; v += 256) row_s[v] = lg[v];
+      for (int v = tid; v < V; v += 256) {
+        const float x = lg[v];
+        row_s[v] = x;
+        if (x > m) { ssum = ssum * exp_sel<FAST>(m - x) + 1.f; m = x; }
+        else ssum += exp_sel<FAST>(x - m);
+      }
     }
-    __syncthreads();
+    // combine (m, s) pairs: warp shuffles, then the 8 warp results
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const float os = __shfl_xor_sync(0xffffffffu, ssum, o);
+      const float nm = fmaxf(m, om);
+      ssum = (nm == -INFINITY) ? 0.f : ssum * exp_sel<FAST>(m - nm) + os * exp_sel<FAST>(om - nm);
+      m = nm;
+    }
+    if (lane == 0) { scratch[warp] = m; scratch[8 + warp] = ssum; }
+    __syncthreads();                       // also publishes row_s
+    float gm = scratch[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) gm = fmaxf(gm, scratch[w]);
+    float gs = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) gs += (scratch[w] == -INFINITY) ? 0.f : scratch[8 + w] * exp_sel<FAST>(scratch[w] - gm);
+    ls = gm + logf(gs);
     lg = row_s;
-  }
-  float ls;
-  if (lse_in) {
-    ls = lse_in[r];
   } else {
-    float m = -INFINITY;
-    for (int v = tid; v < V; v += 256) m = fmaxf(m, lg[v]);
-    m = block_max(m, scratch);
-    float s = 0.f;
-    for (int v = tid; v < V; v += 256) s += expf(lg[v] - m);
-    s = block_sum(s, scratch);
-    ls = m + logf(s);
+    if (staged) {
+      for (int v = tid; v < V; v += 256) row_s[v] = lg[v];
+      __syncthreads();
+      lg = row_s;
+    }
+    if (lse_in) {
+      ls = lse_in[r];
+    } else {
+      float m = -INFINITY;
+      for (int v = tid; v < V; v += 256) m = fmaxf(m, lg[v]);
+      m = block_max(m, scratch);
+      float s2 = 0.f;
+      for (int v = tid; v < V; v += 256) s2 += expf(lg[v] - m);
+      s2 = block_sum(s2, scratch);
+      ls = m + logf(s2);
+    }
   }
   if (tid == 0 && lse_out) lse_out[r] = ls;
   const float sc = scores[r];
   const bool fin = finished[r] != 0;
 
-  // candidate values, in place in shared memory when the row is staged
+  // candidate values, in place in shared memory when the row is staged; the same pass finds each
+  // thread's best candidate (the first "rescan")
+  float tv = INFINITY;     // last candidate taken from this thread's slice
+  int ti = -1;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  float b2v = -INFINITY;   // runner-up of the thread's slice: the first win needs no rescan
+  int b2i = 0x7fffffff;
   if (staged) {
     for (int v = tid; v < V; v += 256) {
       float c;
       if (fin) c = (v == end_id) ? sc : -INFINITY;
       else c = __fadd_rn(sc, __fsub_rn(row_s[v], ls));
-      row_s[v] = c;
+      row_s[v] = c;                         // a thread only ever re-reads its own slice: no barrier needed
+      if (bi == 0x7fffffff || c > bv) { b2v = bv; b2i = bi; bv = c; bi = v; }
+      else if (b2i == 0x7fffffff || c > b2v) { b2v = c; b2i = v; }
     }
-    __syncthreads();
   }
   auto cand = [&](int v) -> float {
     if (staged) return row_s[v];
@@ -175,10 +239,6 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
   // version kept a sorted K-list per thread and was instruction bound on the insertions).
   // Order: value descending, index ascending; a thread scans v ascending, so strict '>' keeps the
   // lowest index among equal values.
-  float tv = INFINITY;     // last candidate taken from this thread's slice
-  int ti = -1;
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
   auto rescan = [&]() {
     bv = -INFINITY;
     bi = 0x7fffffff;
@@ -188,7 +248,7 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
       if (elig && (bi == 0x7fffffff || c > bv)) { bv = c; bi = v; }
     }
   };
-  rescan();
+  if (!staged) rescan();
   for (int rd = 0; rd < K; ++rd) {
     float wvv = bv;
     int wii = bi;
@@ -211,7 +271,8 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
     if (bi == s_win && bi != 0x7fffffff) {   // this thread's candidate was taken: find its next one
       tv = bv;
       ti = bi;
-      rescan();
+      if (b2i != 0x7fffffff) { bv = b2v; bi = b2i; b2i = 0x7fffffff; }    // cached runner-up
+      else rescan();
     }
     __syncthreads();
   }
@@ -267,7 +328,7 @@ inline size_t beam_select_workspace_bytes(int B, int K) { return (size_t)B * K *
 inline int launch_beam_select(const float* scores, const uint8_t* finished, const float* logits,
                               const float* lse_in, float* lse_out, int B, int K, int V, int end_id,
                               void* workspace, float* new_scores, int32_t* back, int32_t* tok,
-                              uint8_t* new_finished, cudaStream_t st) {
+                              uint8_t* new_finished, cudaStream_t st, bool fast = false) {
   if (B <= 0) return 0;
   if (K > V) DIC_FAIL(-4, "beam %d larger than vocabulary %d", K, V);
   float* cv = reinterpret_cast<float*>(workspace);
@@ -276,8 +337,12 @@ inline int launch_beam_select(const float* scores, const uint8_t* finished, cons
   ProfScope prof(P_BEAM_SELECT, st, (double)B * K * V * sizeof(float));
 #define DIC_TOPK_CASE(KK)                                                                                  \
   case KK:                                                                                                 \
-    DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK>, dim3(B * KK), dim3(256), staged ? sizeof(float) * V : 0, \
-                        st, scores, finished, logits, lse_in, lse_out, V, end_id, cv, ci, staged, g_trace_host));         \
+    if (fast)                                                                                              \
+      DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK, true>, dim3(B * KK), dim3(256), staged ? sizeof(float) * V : 0, \
+                          st, scores, finished, logits, lse_in, lse_out, V, end_id, cv, ci, staged, g_trace_host)); \
+    else                                                                                                   \
+      DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK, false>, dim3(B * KK), dim3(256), staged ? sizeof(float) * V : 0, \
+                          st, scores, finished, logits, lse_in, lse_out, V, end_id, cv, ci, staged, g_trace_host));         \
     DIC_LAUNCH_CHECK();                                                                                    \
     DIC_CUDA(launch_pdl(beam_merge_kernel<KK>, dim3(cdiv(B, 4)), dim3(128), 0, st, (const float*)cv,       \
                         (const int*)ci, finished, B, V, end_id, new_scores, back, tok, new_finished,     \

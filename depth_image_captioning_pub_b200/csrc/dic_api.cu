@@ -666,7 +666,7 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
         // row log-sum-exp + per-row top-K in one kernel, then a per-image merge
         DIC_TRY(launch_beam_select(sc[t & 1] + r0, fin[t & 1] + r0, lg, nullptr, lse_t, Bs, K, V, end_id,
                                    ws + lay.cand + r0 * K * (sizeof(float) + sizeof(int)),
-                                   sc[(t + 1) & 1] + r0, back_t, tok_t, fin[(t + 1) & 1] + r0, sst));
+                                   sc[(t + 1) & 1] + r0, back_t, tok_t, fin[(t + 1) & 1] + r0, sst, is_bf16 != 0));
         DIC_CUDA(launch_pdl(beam_reorder_kernel<ST>, dim3(cdiv(Rs * (E + H), 256)), dim3(256), 0, sst,
                             (const ST*)(h_tmp + r0 * H), (const float*)(c_tmp + r0 * H), (const int32_t*)back_t,
                             (const int32_t*)tok_t, reinterpret_cast<const ST*>(pk.Emb()), Xn, XW, E + D,

@@ -61,8 +61,20 @@ __global__ void __launch_bounds__(256) loss_ce_row_kernel(const LossArgs p, int 
     if ((V & 3) == 0) {
       const float4* src4 = reinterpret_cast<const float4*>(lg);
       float4* dst4 = reinterpret_cast<float4*>(row_s);
-      for (int i = tid; i < V / 4; i += 256) {
-        const float4 x = src4[i];            // plain loads: the row may be overwritten below (in-place d_logits)
+      const int n4 = V / 4;
+      int i = tid;
+      for (; i + 3 * 256 < n4; i += 4 * 256) {      // four 16-byte loads in flight per thread
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = src4[i + u * 256];   // plain loads: the row may be overwritten below
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          dst4[i + u * 256] = x[u];
+          m = fmaxf(fmaxf(m, fmaxf(x[u].x, x[u].y)), fmaxf(x[u].z, x[u].w));
+        }
+      }
+      for (; i < n4; i += 256) {
+        const float4 x = src4[i];
         dst4[i] = x;
         m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
       }
