@@ -335,6 +335,8 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// bf16 mode: ex2.approx + rcp.approx (relative error ~1e-6, far below the bf16 storage of what it gates)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
 
 // per-step valid batch sizes, passed to kernels by value
 struct StepSizes {

@@ -122,6 +122,7 @@ static int hproj(const dic_dims& d, const Pack& pk, const ST* h, long long h_ld,
                             d.A + d.D, d.H, pk.bias_db());
   g.sig_lo = d.A;
   g.sig_hi = d.A + d.D;
+  g.fast_act = is_bf16;
   g.tag = 1;
   return gemm(g, st);
 }
@@ -137,10 +138,13 @@ static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long 
   // (as many as it takes to cover the SMs about twice; large row counts need few or none)
   int s;
   if (tc_gemm_eligible(g)) {
-    const long long tiles = (long long)cdiv(rows, kTcBM) * cdiv(4 * d.H, 128);
-    s = (int)((2 * 148 + tiles - 1) / tiles);
+    // 64-column tiles and just enough K splits for one wave: a CTA's time is fixed latency + the store
+    // of its fp32 partial tile (128x128 took 2.1 us of a 4.5 us CTA), and lstm re-reads every partial
+    const long long tiles = (long long)cdiv(rows, kTcBM) * cdiv(4 * d.H, 64);
+    s = (int)(tc_num_sms() / tiles);
     const int kb = cdiv((int)XW, kTcBK);
-    if (s > kb) s = kb;
+    if (s > kb / 2) s = kb / 2;
+    g.bn = 64;
   } else {
     s = pick_splits(rows, 4 * d.H, (int)XW);
   }
@@ -765,26 +769,33 @@ int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void*
   const int bf = dtype == DIC_BF16;
   const size_t es = lay.es;
   const long long XW = (long long)d.E + d.D + d.H;
-  DIC_TRY(launch_copy2d(p->enc_att_w, d.D, base + lay.Wenc, d.D, bf, d.A, d.D, st));
-  DIC_TRY(launch_copy2d(p->w_hh, d.H, base + lay.Whdb, d.H, bf, 4 * d.H, d.H, st));
-  DIC_TRY(launch_copy2d(p->dec_att_w, d.H, base + lay.Whdb + (size_t)4 * d.H * d.H * es, d.H, bf, d.A, d.H, st));
-  DIC_TRY(launch_copy2d(p->fbeta_w, d.H, base + lay.Whdb + (size_t)(4 * d.H + d.A) * d.H * es, d.H, bf, d.D,
-                        d.H, st));
-  DIC_TRY(launch_copy2d(p->w_ih, d.E + d.D, base + lay.Wg, XW, bf, 4 * d.H, d.E + d.D, st));
-  DIC_TRY(launch_copy2d(p->w_hh, d.H, base + lay.Wg + (size_t)(d.E + d.D) * es, XW, bf, 4 * d.H, d.H, st));
-  DIC_TRY(launch_copy2d(p->init_w, d.D, base + lay.Winit, d.D, bf, 2 * d.H, d.D, st));
-  DIC_TRY(launch_copy2d(p->lin_w, d.H, base + lay.Wout, d.H, bf, d.V, d.H, st));
-  DIC_TRY(launch_copy2d(p->embed_w, d.E, base + lay.Emb, d.E, bf, d.V, d.E, st));
-  DIC_TRY(launch_copy2d(p->enc_att_b, d.A, base + lay.b_enc, d.A, 0, 1, d.A, st));
-  DIC_TRY(launch_copy2d(p->dec_att_b, d.A, base + lay.bias_db, d.A, 0, 1, d.A, st));
-  DIC_TRY(launch_copy2d(p->fbeta_b, d.D, base + lay.bias_db + sizeof(float) * d.A, d.D, 0, 1, d.D, st));
-  add_vec_kernel<<<cdiv(4 * d.H, 256), 256, 0, st>>>(p->b_ih, p->b_hh,
-                                                     reinterpret_cast<float*>(base + lay.bias_g), 4 * d.H);
+  PackJobs jobs;
+  jobs.n = 0;
+  auto add = [&](const float* src, long long src_ld, void* dst, long long dst_ld, int dst_bf16, int R, int C,
+                 const float* src2 = nullptr) {
+    PackJob& j = jobs.j[jobs.n++];
+    j.src = src; j.src2 = src2; j.dst = dst; j.src_ld = src_ld; j.dst_ld = dst_ld; j.R = R; j.C = C;
+    j.dst_bf16 = dst_bf16;
+  };
+  add(p->enc_att_w, d.D, base + lay.Wenc, d.D, bf, d.A, d.D);
+  add(p->w_hh, d.H, base + lay.Whdb, d.H, bf, 4 * d.H, d.H);
+  add(p->dec_att_w, d.H, base + lay.Whdb + (size_t)4 * d.H * d.H * es, d.H, bf, d.A, d.H);
+  add(p->fbeta_w, d.H, base + lay.Whdb + (size_t)(4 * d.H + d.A) * d.H * es, d.H, bf, d.D, d.H);
+  add(p->w_ih, d.E + d.D, base + lay.Wg, XW, bf, 4 * d.H, d.E + d.D);
+  add(p->w_hh, d.H, base + lay.Wg + (size_t)(d.E + d.D) * es, XW, bf, 4 * d.H, d.H);
+  add(p->init_w, d.D, base + lay.Winit, d.D, bf, 2 * d.H, d.D);
+  add(p->lin_w, d.H, base + lay.Wout, d.H, bf, d.V, d.H);
+  add(p->embed_w, d.E, base + lay.Emb, d.E, bf, d.V, d.E);
+  add(p->enc_att_b, d.A, base + lay.b_enc, d.A, 0, 1, d.A);
+  add(p->dec_att_b, d.A, base + lay.bias_db, d.A, 0, 1, d.A);
+  add(p->fbeta_b, d.D, base + lay.bias_db + sizeof(float) * d.A, d.D, 0, 1, d.D);
+  add(p->b_ih, 4 * d.H, base + lay.bias_g, 4 * d.H, 0, 1, 4 * d.H, p->b_hh);     // b_ih + b_hh
+  add(p->init_b, 2 * d.H, base + lay.b_init, 2 * d.H, 0, 1, 2 * d.H);
+  add(p->lin_b, d.V, base + lay.b_out, d.V, 0, 1, d.V);
+  add(p->full_att_w, d.A, base + lay.w_full, d.A, 0, 1, d.A);
+  add(p->full_att_b, 1, base + lay.b_full, 1, 0, 1, 1);
+  pack_jobs_kernel<<<dim3(64, jobs.n), 256, 0, st>>>(jobs);
   DIC_LAUNCH_CHECK();
-  DIC_TRY(launch_copy2d(p->init_b, 2 * d.H, base + lay.b_init, 2 * d.H, 0, 1, 2 * d.H, st));
-  DIC_TRY(launch_copy2d(p->lin_b, d.V, base + lay.b_out, d.V, 0, 1, d.V, st));
-  DIC_TRY(launch_copy2d(p->full_att_w, d.A, base + lay.w_full, d.A, 0, 1, d.A, st));
-  DIC_TRY(launch_copy2d(p->full_att_b, 1, base + lay.b_full, 1, 0, 1, 1, st));
   return 0;
 }
 

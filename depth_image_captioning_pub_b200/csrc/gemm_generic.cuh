@@ -33,6 +33,8 @@ struct GemmArgs {
   float bias_scale;
   int sig_lo, sig_hi;     // apply sigmoid to columns [sig_lo, sig_hi)
   int tag;                // call-site id for the timeline trace
+  int bn;                 // tcgen05 engine: N tile width (32/64/128), 0 = chosen from the shape
+  int fast_act;           // sigmoid through ex2.approx / rcp.approx (bf16 mode)
 };
 
 inline GemmArgs gemm_args_nt(const void* A, int a_bf16, long long lda, const void* B, int b_bf16,

@@ -140,6 +140,8 @@ struct TcArgs {
   int sig_lo, sig_hi;
   int tiles_m, tiles_n;
   int tag;
+  int fast_act;
+  int dbg;               // DIC_GEMM_DEBUG=1: CTA 0 prints a globaltimer breakdown of its first tile
   TraceRec* trace;
 };
 
@@ -156,6 +158,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(!B_MN || BN >= 64, "MN-major B needs whole 64-wide blocks");
   extern __shared__ uint8_t smem_raw[];
   Trace trace(p.trace);
+  __shared__ unsigned long long dbg_t[12];
+  const bool dbg = p.dbg != 0 && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) dbg_t[0] = gtimer();
   constexpr uint32_t A_BYTES = kTcBM * kTcBK * 2;
   constexpr uint32_t B_BYTES = BN * kTcBK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -200,11 +205,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (dbg && threadIdx.x == 0) dbg_t[1] = gtimer();
   // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous
   // kernel's tail; operands and the output buffer may only be touched after it has completed.
   pdl_wait();
   pdl_trigger();
   trace.mark();
+  if (dbg && threadIdx.x == 0) dbg_t[2] = gtimer();
 
   // tile index -> (split, m block, n block); n fastest so that concurrent CTAs share the A tile in L2
   auto decode = [&](int t, int& split, int& m0, int& n0, int& kb0, int& kb1) {
@@ -244,6 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
+        if (dbg && t == (int)blockIdx.x) dbg_t[3] = gtimer();
       }
     }
   } else if (warp == 1) {
@@ -266,6 +274,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (dbg && t == (int)blockIdx.x && kb == kb0) dbg_t[4] = gtimer();
+          if (dbg && t == (int)blockIdx.x && kb == kb1 - 1) dbg_t[5] = gtimer();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           const uint64_t adesc = A_MN ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
@@ -278,6 +288,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar(acc));       // accumulator complete
+        if (dbg && t == (int)blockIdx.x) dbg_t[6] = gtimer();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -293,7 +304,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       int split, m0, n0, kb0, kb1;
       decode(t, split, m0, n0, kb0, kb1);
+      // the bias of this thread's store columns is fetched while the accumulator is still being computed
+      float bzc[COLS / 32][4];
+      {
+        const bool pre_bias = p.bias != nullptr && split == 0 && grp < GROUPS;
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) {
+          const int n = n0 + grp * COLS + c * 32 + (lane & 7) * 4;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) bzc[c][e] = (pre_bias && n + e < p.N) ? __ldg(p.bias + n + e) : 0.f;
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (dbg && t == (int)blockIdx.x && warp == 4 && lane == 0) dbg_t[7] = gtimer();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[COLS / 32][32];
       if (grp < GROUPS) {
@@ -306,6 +329,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (dbg && t == (int)blockIdx.x && warp == 4 && lane == 0) dbg_t[8] = gtimer();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
       // Stores go through a per-warp shared-memory transpose: after tcgen05.ld a thread owns one ROW
@@ -348,7 +372,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!plain) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (add_bias && n + e < p.N) bz[e] = __ldg(p.bias + n + e);
+              bz[e] = bzc[c][e];
               sg[e] = (n + e >= p.sig_lo) && (n + e < p.sig_hi);
             }
             any_sig = (nb + 32 > p.sig_lo) && (nb < p.sig_hi);          // warp-uniform
@@ -365,10 +389,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 v.z = fmaf(v.z, p.alpha, bz[2]); v.w = fmaf(v.w, p.alpha, bz[3]);
               }
               if constexpr (MODE.value == 2) {
-                if (sg[0]) v.x = sigmoidf_acc(v.x);
-                if (sg[1]) v.y = sigmoidf_acc(v.y);
-                if (sg[2]) v.z = sigmoidf_acc(v.z);
-                if (sg[3]) v.w = sigmoidf_acc(v.w);
+                if (p.fast_act) {
+                  if (sg[0]) v.x = sigmoidf_fast(v.x);
+                  if (sg[1]) v.y = sigmoidf_fast(v.y);
+                  if (sg[2]) v.z = sigmoidf_fast(v.z);
+                  if (sg[3]) v.w = sigmoidf_fast(v.w);
+                } else {
+                  if (sg[0]) v.x = sigmoidf_acc(v.x);
+                  if (sg[1]) v.y = sigmoidf_acc(v.y);
+                  if (sg[2]) v.z = sigmoidf_acc(v.z);
+                  if (sg[3]) v.w = sigmoidf_acc(v.w);
+                }
               }
               if (rr < rows_valid && n < p.N) {
                 if constexpr (OUT.value == 0) {
@@ -413,6 +444,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
         }
       }
+      if (dbg && t == (int)blockIdx.x && warp == 4 && lane == 0) dbg_t[9] = gtimer();
     }
   }
 
@@ -420,6 +452,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+  if (dbg && threadIdx.x == 0) {
+    const unsigned long long t0 = dbg_t[0];
+    printf("[gemm dbg] M=%d N=%d K=%d BN=%d grid=%d | setup %llu wait %llu tma_issued %llu full0 %llu fullN %llu commit %llu tfull %llu tmem_ld %llu stores %llu exit %llu (ns from entry)\n",
+           p.M, p.N, p.K, BN, (int)gridDim.x, dbg_t[1] - t0, dbg_t[2] - t0, dbg_t[3] - t0, dbg_t[4] - t0, dbg_t[5] - t0,
+           dbg_t[6] - t0, dbg_t[7] - t0, dbg_t[8] - t0, dbg_t[9] - t0, gtimer() - t0);
   }
   trace.end(TK_GEMM_TC + 100 * p.tag);
 }
@@ -537,7 +575,13 @@ inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   p.tiles_m = cdiv(g.M, kTcBM);
   p.tiles_n = cdiv(g.N, BN);
   p.tag = g.tag;
+  p.fast_act = g.fast_act;
   p.trace = g_trace_host;
+  {
+    static int dbg_env = -1;
+    if (dbg_env < 0) { const char* e = getenv("DIC_GEMM_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+    p.dbg = dbg_env;
+  }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int grid = (int)(total < tc_num_sms() ? total : tc_num_sms());
   ProfScope prof(P_GEMM_TC, st);
@@ -559,6 +603,7 @@ inline int tc_gemm(const GemmArgs& g, cudaStream_t st) {
   int bn = 128;
   if (tm * cdiv(g.N, 128) * splits < half && g.N > 64) bn = 64;
   if (bn == 64 && tm * cdiv(g.N, 64) * splits < half && g.N > 32 && !b_mn) bn = 32;
+  if (g.bn == 128 || g.bn == 64 || (g.bn == 32 && !b_mn)) bn = g.bn;
   if (bn == 128) return tc_gemm_bn<128>(g, st);
   if (bn == 64) return tc_gemm_bn<64>(g, st);
   return tc_gemm_bn<32>(g, st);

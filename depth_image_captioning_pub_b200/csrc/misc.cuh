@@ -259,6 +259,42 @@ inline int launch_copy2d(const float* src, long long src_ld, void* dst, long lon
   return 0;
 }
 
+// ---- weight packing in ONE launch: a table of 2-D copy/convert jobs (blockIdx.y = job) ----------------
+// (17 separate copy kernels cost ~55 us of launch latency per training step; the data is 10 MB)
+struct PackJob {
+  const float* src;
+  const float* src2;       // optional second addend (b_ih + b_hh)
+  void* dst;
+  long long src_ld, dst_ld;
+  int R, C, dst_bf16;
+};
+constexpr int kMaxPackJobs = 20;
+struct PackJobs {
+  PackJob j[kMaxPackJobs];
+  int n;
+};
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJobs jobs) {
+  const PackJob& jb = jobs.j[blockIdx.y];
+  const size_t n = (size_t)jb.R * jb.C;
+  const bool dense = jb.src_ld == jb.C && jb.dst_ld == jb.C;
+  if (dense && jb.dst_bf16 && !jb.src2 && n % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(jb.src) | reinterpret_cast<uintptr_t>(jb.dst)) & 15) == 0) {
+    const size_t n8 = n / 8;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+      float v[8];
+      load8_stream<float>(jb.src + i * 8, v);
+      store8<bf16>(reinterpret_cast<bf16*>(jb.dst) + i * 8, v);
+    }
+    return;
+  }
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const size_t r = i / jb.C, c = i - r * jb.C;
+    float v = jb.src[r * jb.src_ld + c];
+    if (jb.src2) v += jb.src2[r * jb.src_ld + c];
+    st_from_float(jb.dst, r * jb.dst_ld + c, v, jb.dst_bf16);
+  }
+}
+
 __global__ void __launch_bounds__(256) add_vec_kernel(const float* a, const float* b, float* dst, int n) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < n) dst[i] = a[i] + b[i];

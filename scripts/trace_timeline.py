@@ -17,6 +17,7 @@ ap.add_argument("--sub", type=int, default=1)
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--rows", type=int, default=70)
 ap.add_argument("--skip", type=int, default=0, help="launches to skip before printing")
+ap.add_argument("--detail", type=int, default=-1, help="kernel id: per-CTA go/exit distribution of one launch")
 args = ap.parse_args()
 L, D, A, E, H, V, T = bench.L, bench.D, bench.A, bench.E, bench.H, bench.V, bench.T
 dev = torch.device("cuda", 0)
@@ -69,11 +70,23 @@ order = np.argsort(rec["t1"], kind="stable")
 rec = rec[order]
 launches = []
 i = 0
+detail_seen = 0
 while i < n:
     j = i
     while j < n and rec["kid"][j] == rec["kid"][i]:
         j += 1
     r = rec[i:j]
+    if args.detail >= 0 and int(r["kid"][0]) == args.detail:
+        detail_seen += 1
+        if detail_seen == 8:      # a launch from the middle of the loop
+            base_t = int(r["t1"].min())
+            go = np.sort((r["t1"].astype(np.int64) - base_t) / 1e3)
+            ex = np.sort((r["t2"].astype(np.int64) - base_t) / 1e3)
+            dur = np.sort((r["t2"].astype(np.int64) - r["t1"].astype(np.int64)) / 1e3)
+            ent = np.sort((r["t0"].astype(np.int64) - base_t) / 1e3)
+            q = lambda a: " ".join(f"{np.percentile(a, p):7.2f}" for p in (0, 10, 50, 90, 100))
+            print(f"detail kid={args.detail}: {len(r)} CTAs; percentiles 0/10/50/90/100 (us rel. first go)")
+            print("  entry:", q(ent)); print("  go   :", q(go)); print("  exit :", q(ex)); print("  go->exit per CTA:", q(dur))
     launches.append((int(r["kid"][0]), j - i, int(r["t0"].min()), int(r["t1"].min()), int(r["t1"].max()),
                      int(r["t2"].min()), int(r["t2"].max())))
     i = j
