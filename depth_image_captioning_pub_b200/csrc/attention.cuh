@@ -378,13 +378,27 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
     attr_set = true;
   }
   {
-    // one CTA per ROW (beam): images*KB CTAs, the KB CTAs of an image share its att1 slab through L2
     ProfScope prof(P_ATTN_ALPHA, st, (double)images * p.L * p.A * sizeof(ST));
     AttnFwdArgs pa = p;
-    pa.rpi = KB;
     pa.trace = g_trace_host;
-    DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, 1>, dim3(images * KB), dim3(kAlphaThreads),
-                        attn_alpha_smem_bytes(p.L, p.A, 1), st, pa));
+    static int per_image = -1;
+    if (per_image < 0) { const char* e = getenv("DIC_ALPHA_PER_IMAGE"); per_image = (e && e[0] == '0') ? 0 : 1; }
+    if (KB > 1 && per_image) {
+      // one CTA per IMAGE computing its KB rows from one read of the att1 slab
+      static bool attr2 = false;
+      if (!attr2) {
+        DIC_CUDA(cudaFuncSetAttribute(attn_alpha_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr2 = true;
+      }
+      pa.rpi = 0;
+      DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, KB>, dim3(images), dim3(kAlphaThreads),
+                          attn_alpha_smem_bytes(p.L, p.A, KB), st, pa));
+    } else {
+      // one CTA per ROW (beam): images*KB CTAs, the KB CTAs of an image share its att1 slab through L2
+      pa.rpi = KB;
+      DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, 1>, dim3(images * KB), dim3(kAlphaThreads),
+                          attn_alpha_smem_bytes(p.L, p.A, 1), st, pa));
+    }
     DIC_LAUNCH_CHECK();
   }
   {

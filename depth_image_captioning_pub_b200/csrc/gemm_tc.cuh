@@ -159,7 +159,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   Trace trace(p.trace);
   __shared__ unsigned long long dbg_t[12];
-  const bool dbg = p.dbg != 0 && blockIdx.x == 0;
+#ifdef DIC_GEMM_DEBUG_BUILD
+#ifdef DIC_GEMM_DEBUG_BUILD
+  const bool dbg = p.dbg == 1 && blockIdx.x == 0;
+#else
+  constexpr bool dbg = false;      // build with -DDIC_GEMM_DEBUG_BUILD for the DIC_GEMM_DEBUG=1 latency print
+#endif
+#else
+  constexpr bool dbg = false;      // build with -DDIC_GEMM_DEBUG_BUILD for the DIC_GEMM_DEBUG=1 latency print
+#endif
   if (dbg && threadIdx.x == 0) dbg_t[0] = gtimer();
   constexpr uint32_t A_BYTES = kTcBM * kTcBK * 2;
   constexpr uint32_t B_BYTES = BN * kTcBK * 2;
@@ -377,29 +385,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             any_sig = (nb + 32 > p.sig_lo) && (nb < p.sig_hi);          // warp-uniform
           }
-          const int mode = plain ? 0 : (any_sig ? 2 : 1);
-          const int outk = !full ? 3 : (atomic ? 2 : (p.c_bf16 ? 1 : 0));
+          // Few specialisations on purpose: MODE 0 = scale + bias (alpha = 1, bias = 0 when not requested:
+          // four FMAs per store are free next to the store itself), MODE 1 adds the sigmoid columns;
+          // OUT 0/1/2 = 16-byte fp32 / 8-byte bf16 / vector red.add, OUT 3 = scalar tail (any mode).
+          // With all 12 (mode, output) pairs unrolled the BN = 128 kernel was 120 KB of code and its
+          // epilogue ran 30% slower from instruction-cache misses alone.
+          const float al = p.alpha;
+          const int outk = (!full || (any_sig && (atomic || p.c_bf16))) ? 3 : (atomic ? 2 : (p.c_bf16 ? 1 : 0));
           auto run = [&](auto MODE, auto OUT) {
-#pragma unroll
+#pragma unroll(OUT.value == 3 ? 1 : 8)
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + rrow;
               float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + col4);
-              if constexpr (MODE.value >= 1) {
-                v.x = fmaf(v.x, p.alpha, bz[0]); v.y = fmaf(v.y, p.alpha, bz[1]);
-                v.z = fmaf(v.z, p.alpha, bz[2]); v.w = fmaf(v.w, p.alpha, bz[3]);
-              }
-              if constexpr (MODE.value == 2) {
-                if (p.fast_act) {
-                  if (sg[0]) v.x = sigmoidf_fast(v.x);
-                  if (sg[1]) v.y = sigmoidf_fast(v.y);
-                  if (sg[2]) v.z = sigmoidf_fast(v.z);
-                  if (sg[3]) v.w = sigmoidf_fast(v.w);
-                } else {
-                  if (sg[0]) v.x = sigmoidf_acc(v.x);
-                  if (sg[1]) v.y = sigmoidf_acc(v.y);
-                  if (sg[2]) v.z = sigmoidf_acc(v.z);
-                  if (sg[3]) v.w = sigmoidf_acc(v.w);
-                }
+              v.x = fmaf(v.x, al, bz[0]); v.y = fmaf(v.y, al, bz[1]);
+              v.z = fmaf(v.z, al, bz[2]); v.w = fmaf(v.w, al, bz[3]);
+              if constexpr (MODE.value == 1) {
+                // this engine only ever runs in bf16 mode (tc_gemm_eligible): ex2.approx / rcp.approx sigmoid
+                if (sg[0]) v.x = sigmoidf_fast(v.x);
+                if (sg[1]) v.y = sigmoidf_fast(v.y);
+                if (sg[2]) v.z = sigmoidf_fast(v.z);
+                if (sg[3]) v.w = sigmoidf_fast(v.w);
               }
               if (rr < rows_valid && n < p.N) {
                 if constexpr (OUT.value == 0) {
@@ -433,13 +438,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           using I2 = std::integral_constant<int, 2>;
           using I3 = std::integral_constant<int, 3>;
           if (outk == 0) {
-            if (mode == 0) run(I0{}, I0{}); else if (mode == 1) run(I1{}, I0{}); else run(I2{}, I0{});
+            if (any_sig) run(I1{}, I0{}); else run(I0{}, I0{});
           } else if (outk == 1) {
-            if (mode == 0) run(I0{}, I1{}); else if (mode == 1) run(I1{}, I1{}); else run(I2{}, I1{});
+            run(I0{}, I1{});
           } else if (outk == 2) {
-            if (mode == 0) run(I0{}, I2{}); else run(I2{}, I2{});
+            run(I0{}, I2{});
           } else {
-            if (mode == 0) run(I0{}, I3{}); else run(I2{}, I3{});
+            run(I1{}, I3{});
           }
           __syncwarp();
         }
@@ -579,7 +584,7 @@ inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   p.trace = g_trace_host;
   {
     static int dbg_env = -1;
-    if (dbg_env < 0) { const char* e = getenv("DIC_GEMM_DEBUG"); dbg_env = (e && e[0] == '1') ? 1 : 0; }
+    if (dbg_env < 0) { const char* e = getenv("DIC_GEMM_DEBUG"); dbg_env = (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 0; }
     p.dbg = dbg_env;
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;

@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -19,12 +20,15 @@ PRECISIONS = {"fp32": _lib.DIC_F32, "float32": _lib.DIC_F32, "bf16": _lib.DIC_BF
 def batch_sizes_from_lengths(lengths: Sequence[int]) -> List[int]:
     """bs_valid per decoder step for caption lengths (incl. <start>) sorted descending
     (depth_models.py:170,182; util.py:95)."""
-    dec = [int(l) - 1 for l in lengths]
-    if not dec or min(dec) < 1:
+    dec = np.asarray([int(l) for l in lengths], dtype=np.int64) - 1
+    if dec.size == 0 or dec.min() < 1:
         raise ValueError("every caption needs at least <start> and one target token")
-    if any(dec[i] < dec[i + 1] for i in range(len(dec) - 1)):
+    if np.any(dec[:-1] < dec[1:]):
         raise ValueError("lengths must be sorted in descending order (as collate_func does)")
-    return [sum(1 for l in dec if l > t) for t in range(max(dec))]
+    # number of captions still active at step t = #{b : dec[b] > t}
+    counts = np.bincount(dec, minlength=int(dec.max()) + 1)
+    active = dec.size - np.cumsum(counts)[:int(dec.max())]
+    return [int(x) for x in active]
 
 
 def _params_struct(tensors: Sequence[torch.Tensor]) -> Params:

@@ -32,20 +32,29 @@ def host_dev(fn, n=10):
         th += t1 - t0; td += e0.elapsed_time(e1) * 1e-3
     return th / n * 1e3, td / n * 1e3
 
-for s in (1, 2):
+opt = torch.optim.AdamW(list(m.parameters()), lr=1e-3, fused=True)
+for s in (1,):
     lib.dic_set_substreams(s)
     def fwd():
         out, alphas = m(F_rgb, F_dep, caps, lengths)
         return out, alphas
     print(f"S={s} train forward: host %.3f ms, device %.3f ms" % host_dev(fwd))
     def fb():
-        out, alphas = m(F_rgb, F_dep, caps, lengths)
-        loss = torch.nn.functional.cross_entropy(out.data, targets, ignore_index=V - 1)
-        loss = loss + 0.7 * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+        loss = m.forward_loss(F_rgb, F_dep, caps, lengths, ignore_index=V - 1, lam=0.7)
         loss.backward()
         F_dep.grad = None
         m.zero_grad(set_to_none=True)
     print(f"S={s} train fwd+loss+bwd: host %.3f ms, device %.3f ms" % host_dev(fb))
+    def full():
+        loss = m.forward_loss(F_rgb, F_dep, caps, lengths, ignore_index=V - 1, lam=0.7)
+        loss.backward()
+        opt.step(); opt.zero_grad(set_to_none=True); F_dep.grad = None
+    print(f"S={s} full step: host %.3f ms, device %.3f ms" % host_dev(full))
+    import cProfile, pstats
+    pr = cProfile.Profile(); pr.enable()
+    for _ in range(20): full()
+    pr.disable(); torch.cuda.synchronize()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
     m.eval(); m.cache_packed_weights = True
     voc = O.synthetic_vocab(V)
     fr, fd = F_rgb[:128].contiguous(), F_dep[:128].detach().contiguous()
