@@ -370,6 +370,14 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
 }
 
 template <typename ST, int KB>
+inline int launch_attn_context_bulk(const AttnFwdArgs& p, int images, cudaStream_t st);   // attention_bulk.cuh
+inline bool bulk_ctx_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DIC_BULK_CTX"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <typename ST, int KB>
 inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -400,6 +408,10 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
                           attn_alpha_smem_bytes(p.L, p.A, 1), st, pa));
     }
     DIC_LAUNCH_CHECK();
+  }
+  if (KB >= 3 && p.mode == DIC_ATTN_SOFT && bulk_ctx_enabled()) {
+    // several beams per image: bulk-copy / shared-memory staged variant (attention_bulk.cuh)
+    return launch_attn_context_bulk<ST, KB>(p, images, st);
   }
   {
     // algorithmic bytes of the context pass: the annotations once per image-step

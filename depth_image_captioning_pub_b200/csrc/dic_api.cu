@@ -1,6 +1,7 @@
 // C-ABI entry points (include/dic.h) and the host-side orchestration of the decoder path.
 // One translation unit: kernels are header templates, this file instantiates and sequences them.
 #include "attention.cuh"
+#include "attention_bulk.cuh"
 #include "common.cuh"
 #include "decode.cuh"
 #include "dfeat_tc.cuh"
