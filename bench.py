@@ -32,6 +32,15 @@ L, D, A, E, H, V, T = 196, 2048, 128, 128, 128, 10000, 20
 LAM = 0.7   # doubly-stochastic regulariser weight (depth_train.py:216)
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ----------------------------------------------------------------------------------------------
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -165,7 +174,7 @@ def run_reference(args):
         "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus, batch):
@@ -193,7 +202,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL banners / debug lines must not reach stdout
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -213,7 +222,7 @@ def run_b200(args):
     F_dep = F_dep_h.to(dev).requires_grad_(True)     # the depth CNN is trained: dL/dF_depth is part of the step
     caps = caps_h.to(dev)
     from depth_image_captioning_pub_b200.distributed import FlatGradAllReduce
-    allreduce = FlatGradAllReduce(params) if world > 1 else None
+    allreduce = FlatGradAllReduce(params, module=m) if world > 1 else None
 
     def train_step(fr, fd, cp):
         if args.unfused_loss:       # the reference loop's own loss expression on the returned logits
@@ -361,7 +370,7 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -384,6 +393,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    # stdout carries exactly ONE line, the JSON record: everything else that libraries print there
+    # (e.g. the "NCCL version ..." banner, written by C code) is sent to stderr for the whole run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         run_reference(args)
     else:

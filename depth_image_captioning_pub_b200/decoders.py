@@ -76,6 +76,7 @@ class _DecoderBase(nn.Module):
         if eng is None:
             eng = Engine(L, D, A, E, H, V, self.precision, device)
             self._engines[key] = eng
+        eng.use_flat_grads = bool(getattr(self, "flat_grads", False))
         return eng
 
     def _check_feats(self, features, depth_features):

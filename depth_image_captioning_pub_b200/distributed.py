@@ -32,10 +32,18 @@ def shard_sorted_batch(lengths: Sequence[int], rank: int, world: int) -> List[in
 
 
 class FlatGradAllReduce:
-    """One flat fp32 buffer for all gradients -> a single (NCCL) all-reduce per step."""
+    """One flat fp32 buffer for all gradients -> a single (NCCL) all-reduce per step.
 
-    def __init__(self, params: Sequence[torch.Tensor]):
+    With `module=` (a decoder of this package) the library's backward writes the 17 parameter
+    gradients straight into one flat buffer and `p.grad` aliases it, so the all-reduce (NCCL: AVG)
+    runs in place: no gather / scatter copies.  Parameters whose gradients are not in that buffer
+    (extra trainable tensors, or a step where the aliasing did not happen) take the copy path."""
+
+    def __init__(self, params: Sequence[torch.Tensor], module=None):
         self.params = [p for p in params]
+        self.module = module
+        if module is not None:
+            module.flat_grads = True
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -45,7 +53,29 @@ class FlatGradAllReduce:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
 
+    def _in_place(self, average: bool, group) -> bool:
+        m = self.module
+        if m is None:
+            return False
+        engines = [e for e in getattr(m, "_engines", {}).values() if e.grad_flat is not None and e._grad_ptrs]
+        if len(engines) != 1:
+            return False
+        e = engines[0]
+        ptrs = e._grad_ptrs
+        grads = [p.grad for p in self.params]
+        if any(g is None or g.data_ptr() not in ptrs for g in grads) or len(grads) != len(ptrs):
+            return False
+        if average and dist.get_backend(group) == "nccl":
+            dist.all_reduce(e.grad_flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(e.grad_flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                e.grad_flat.mul_(1.0 / dist.get_world_size(group))
+        return True
+
     def __call__(self, average: bool = True, group=None) -> None:
+        if self._in_place(average, group):
+            return
         world = dist.get_world_size(group)
         for p, v in zip(self.params, self.views):
             if p.grad is None:

@@ -58,6 +58,11 @@ class Engine:
         self.pack = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self._pack_key = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
+        # optional: all parameter gradients written into ONE flat fp32 buffer (data-parallel training:
+        # the NCCL all-reduce then runs on it in place, no gather / scatter copies)
+        self.use_flat_grads = False
+        self.grad_flat: Optional[torch.Tensor] = None
+        self._grad_ptrs: Optional[set] = None      # data pointers of the views handed to autograd
 
     # ---- weights -------------------------------------------------------------------------
     def ensure_packed(self, params: Sequence[torch.Tensor], allow_cached: bool = False) -> None:
@@ -122,7 +127,10 @@ class Engine:
         """d_logits: float32, or the storage dtype of the mode (what the fused loss head writes)."""
         d = self.dims
         B, T = f_rgb.shape[0], len(batch_sizes)
-        grads = [torch.empty(s, dtype=torch.float32, device=self.device) for s in param_shapes]
+        if self.use_flat_grads:
+            grads = self._flat_grad_views(param_shapes)
+        else:
+            grads = [torch.empty(s, dtype=torch.float32, device=self.device) for s in param_shapes]
         d_feats = torch.empty(B, d.L, d.D, dtype=f_rgb.dtype, device=self.device) if need_dfeat else None
         gs = _params_struct(grads)
         bs = (C.c_int32 * T)(*batch_sizes)
@@ -134,6 +142,22 @@ class Engine:
                 _lib.ptr(dropout_mask), C.byref(gs), _lib.ptr(d_feats), _lib.ptr(ws), ws.numel(),
                 _lib.stream_ptr(self.device)))
         return grads, d_feats
+
+    def _flat_grad_views(self, param_shapes) -> List[torch.Tensor]:
+        """Fresh view tensors into the persistent flat gradient buffer (autograd's AccumulateGrad takes
+        them over as .grad without a copy, so p.grad aliases the flat buffer after backward)."""
+        n = sum(int(np.prod(s)) for s in param_shapes)
+        if self.grad_flat is None or self.grad_flat.numel() != n:
+            self.grad_flat = torch.empty(n, dtype=torch.float32, device=self.device)
+        views, o = [], 0
+        for s in param_shapes:
+            k = int(np.prod(s))
+            views.append(self.grad_flat[o:o + k].view(s))
+            o += k
+        # keep no reference to the views: AccumulateGrad only takes a gradient over without a copy when
+        # nobody else holds it
+        self._grad_ptrs = {v.data_ptr() for v in views}
+        return views
 
     def caption_loss(self, logits, captions, batch_sizes, ignore_index: int, alphas, lam: float):
         """Fused CE + doubly-stochastic regulariser (dic_caption_loss).

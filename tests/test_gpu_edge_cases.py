@@ -114,3 +114,40 @@ def test_malformed_inputs_fail_loudly(cuda_device):
         m(fr.double(), fd.double(), cp, cfg["lengths"])  # unsupported dtype
     with pytest.raises((P.DicError, ValueError)):
         m(fr, fd, cp[:, :5].contiguous(), cfg["lengths"])   # captions shorter than the lengths say
+
+
+def test_flat_grad_buffer_aliases_param_grads(cuda_device):
+    """flat_grads: backward writes the 17 parameter gradients into one flat buffer and p.grad aliases
+    it (what FlatGradAllReduce(module=...) all-reduces in place); values equal the default path."""
+    from test_gpu_parity import CASES, build_module, make_case
+    cfg = dict(CASES["small_ragged"])
+    lengths = cfg["lengths"]
+    w, F_rgb, F_dep, caps = make_case(**cfg)
+    V = cfg["V"]
+
+    def run(flat):
+        m = build_module(P.CD_RNNDecoderWithSoftAttention, w, cuda_device).eval()
+        m.flat_grads = flat
+        loss = m.forward_loss(F_rgb.to(cuda_device), F_dep.to(cuda_device), caps.to(cuda_device), lengths,
+                              ignore_index=V - 1)
+        loss.backward()
+        return m
+
+    ref, got = run(False), run(True)
+    eng = next(iter(got._engines.values()))
+    assert eng.grad_flat is not None
+    lo, hi = eng.grad_flat.data_ptr(), eng.grad_flat.data_ptr() + eng.grad_flat.numel() * 4
+    n = 0
+    for (k, p), (_, q) in zip(got.named_parameters(), ref.named_parameters()):
+        assert lo <= p.grad.data_ptr() < hi, k
+        # (weight gradients use atomic split-K: equal up to the fp32 summation order)
+        assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7 + 1e-5 * float(q.grad.abs().max())), k
+        n += p.numel()
+    assert n == eng.grad_flat.numel()
+    # a second step re-uses the buffer after zero_grad(set_to_none=True)
+    got.zero_grad(set_to_none=True)
+    got.forward_loss(F_rgb.to(cuda_device), F_dep.to(cuda_device), caps.to(cuda_device), lengths,
+                     ignore_index=V - 1).backward()
+    for (k, p), (_, q) in zip(got.named_parameters(), ref.named_parameters()):
+        assert lo <= p.grad.data_ptr() < hi, k
+        assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7 + 1e-5 * float(q.grad.abs().max())), k
