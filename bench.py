@@ -212,7 +212,8 @@ def run_b200(args):
     m.precision = args.precision
     m = m.to(dev).train()
     params = [p for p in m.parameters()]
-    opt = torch.optim.AdamW(params, lr=1e-3, fused=True)
+    # the reference steps torch.optim.AdamW(lr=1e-3) (depth_train.py:136-137); same rule, one library launch
+    opt = P.FusedAdamW(params, lr=1e-3) if not args.torch_adamw else torch.optim.AdamW(params, lr=1e-3, fused=True)
     feat_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
     F_rgb_h, F_dep_h, caps_h, lengths = synthetic_batch(B, 1235 + rank, feat_dtype)
     F_rgb_h, F_dep_h, caps_h = F_rgb_h.pin_memory(), F_dep_h.pin_memory(), caps_h.pin_memory()
@@ -388,6 +389,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--unfused-loss", action="store_true",
                     help="compute the loss with torch ops on the returned logits instead of forward_loss")
+    ap.add_argument("--torch-adamw", action="store_true", help="step torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-beam", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -12,7 +12,10 @@ from .decoders import (CD_RNNDecoderWithHardAttention, CD_RNNDecoderWithSoftAtte
                        MD_RNNDecoderWithHardAttention, MD_RNNDecoderWithSoftAttention,
                        RNNDecoderWithHardAttention, RNNDecoderWithSoftAttention)
 
+from .optim import FusedAdamW  # noqa: F401
+
 __all__ = [
+    "FusedAdamW",
     "DicError", "Gumbel_softmax", "Hard_Attention", "Soft_Attention",
     "CD_RNNDecoderWithHardAttention", "CD_RNNDecoderWithSoftAttention",
     "MD_RNNDecoderWithHardAttention", "MD_RNNDecoderWithSoftAttention",

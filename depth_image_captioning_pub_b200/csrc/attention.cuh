@@ -40,6 +40,7 @@ struct AttnFwdArgs {
   long long alpha_stride;
   bf16* alpha16_out;    // optional bf16 copy (A operand of the fused dL/dF GEMM), row r at + r*alpha16_stride
   long long alpha16_stride;
+  int alpha16_width;    // padded row width Lp >= L: columns [L, Lp) are written as zeros
   float* z_out;         // [rows, D] fp32 or null (saved for backward)
   void* zg_out;         // ST, row r at zg_out + r*zg_stride
   long long zg_stride;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
     for (int l = lane; l < L; l += 32) ao[l] = e[l];
     if (p.alpha16_out) {
       bf16* a16 = p.alpha16_out + (size_t)(row0 + j) * p.alpha16_stride;
-      for (int l = lane; l < L; l += 32) a16[l] = __float2bfloat16_rn(e[l]);
+      for (int l = lane; l < p.alpha16_width; l += 32) a16[l] = __float2bfloat16_rn(l < L ? e[l] : 0.f);
     }
   }
   trace.end(TK_ALPHA);

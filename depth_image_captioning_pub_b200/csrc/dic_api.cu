@@ -198,9 +198,11 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
 
   // invalid (b >= bs_valid) rows of the step buffers must stay finite zeros: the post-loop
   // weight-gradient GEMMs run over all T*B rows.
-  DIC_CUDA(cudaMemsetAsync(XH, 0, ((size_t)T * B + B) * XW * sizeof(ST), st));
+  // (a batch of equal-length captions writes every row of these buffers: nothing to clear)
+  const bool ragged = sizes.n[T - 1] < B;
+  if (ragged) DIC_CUDA(cudaMemsetAsync(XH, 0, ((size_t)T * B + B) * XW * sizeof(ST), st));
   bf16* alpha16 = is_bf16 ? reinterpret_cast<bf16*>(ws + lay.alpha16) : nullptr;
-  if (alpha16) DIC_CUDA(cudaMemsetAsync(alpha16, 0, (size_t)T * B * lay.Lp * 2, st));
+  if (alpha16 && ragged) DIC_CUDA(cudaMemsetAsync(alpha16, 0, (size_t)T * B * lay.Lp * 2, st));
 
   const ST* F = nullptr;
   bf16* mean16 = is_bf16 ? reinterpret_cast<bf16*>(ws + lay.meanF16) : nullptr;
@@ -254,6 +256,7 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
       a.alpha_stride = (long long)T * d.L;
       a.alpha16_out = alpha16 ? alpha16 + ((size_t)r0 * T + t) * lay.Lp : nullptr;
       a.alpha16_stride = (long long)T * lay.Lp;
+      a.alpha16_width = lay.Lp;
       a.z_out = Z + ((size_t)t * B + r0) * d.D;
       a.zg_out = X + d.E;
       a.zg_stride = (long long)XW;
@@ -331,13 +334,17 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 
   if (attn_mode == DIC_ATTN_GUMBEL_MAX) DIC_FAIL(-1, "gumbel-max (Hard_sample) is a no_grad path");
 
-  DIC_CUDA(cudaMemsetAsync(G, 0, TB * GW * sizeof(ST), st));
-  DIC_CUDA(cudaMemsetAsync(DZ, 0, TB * D * sizeof(ST), st));
-  DIC_CUDA(cudaMemsetAsync(de, 0, TB * L * sizeof(float), st));
+  // rows of inactive (t, b) pairs must read as zeros in the post-loop contractions over all T*B rows;
+  // with equal-length captions every row is written by the loop below and nothing needs clearing
+  if (sizes.n[T - 1] < B) {
+    DIC_CUDA(cudaMemsetAsync(G, 0, TB * GW * sizeof(ST), st));
+    DIC_CUDA(cudaMemsetAsync(DZ, 0, TB * D * sizeof(ST), st));
+    DIC_CUDA(cudaMemsetAsync(de, 0, TB * L * sizeof(float), st));
+    DIC_CUDA(cudaMemsetAsync(dwfull_part, 0, sizeof(float) * TB * A, st));
+    DIC_CUDA(cudaMemsetAsync(dbfull_part, 0, sizeof(float) * TB, st));
+  }
   DIC_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * B * H, st));
   DIC_CUDA(cudaMemsetAsync(dc, 0, sizeof(float) * B * H, st));
-  DIC_CUDA(cudaMemsetAsync(dwfull_part, 0, sizeof(float) * TB * A, st));
-  DIC_CUDA(cudaMemsetAsync(dbfull_part, 0, sizeof(float) * TB, st));
 
   // bf16 mode: the two contractions over d_logits take a bf16 copy (tensor-core operand)
   const void* dl = d_logits;
@@ -797,6 +804,38 @@ int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void*
   add(p->full_att_b, 1, base + lay.b_full, 1, 0, 1, 1);
   pack_jobs_kernel<<<dim3(64, jobs.n), 256, 0, st>>>(jobs);
   DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+int dic_adamw_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const long long* sizes, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream) {
+  if (n < 0 || (n > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes))) DIC_FAIL(-1, "null argument");
+  if (step < 1) DIC_FAIL(-1, "step counts from 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  for (int base = 0; base < n; base += kMaxOptTensors) {
+    AdamWJobs a;
+    memset(&a, 0, sizeof(a));
+    a.count = n - base < kMaxOptTensors ? n - base : kMaxOptTensors;
+    long long biggest = 0;
+    for (int i = 0; i < a.count; ++i) {
+      a.p[i] = params[base + i]; a.g[i] = grads[base + i]; a.m[i] = exp_avg[base + i]; a.v[i] = exp_avg_sq[base + i];
+      a.n[i] = sizes[base + i];
+      if (!a.p[i] || !a.g[i] || !a.m[i] || !a.v[i] || a.n[i] < 0) DIC_FAIL(-1, "bad tensor %d", base + i);
+      if (a.n[i] > biggest) biggest = a.n[i];
+    }
+    a.lr_wd = lr * weight_decay;
+    a.one_m_b1 = 1.f - beta1; a.b2 = beta2; a.one_m_b2 = 1.f - beta2;
+    a.step_size = (float)((double)lr / bc1);
+    a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    a.eps = eps;
+    long long bx = (biggest / 4 + 255) / 256;
+    if (bx > 148) bx = 148;
+    if (bx < 1) bx = 1;
+    adamw_kernel<<<dim3((unsigned)bx, a.count), 256, 0, st>>>(a);
+    DIC_LAUNCH_CHECK();
+  }
   return 0;
 }
 

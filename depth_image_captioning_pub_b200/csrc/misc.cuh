@@ -295,6 +295,60 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJobs jobs) {
   }
 }
 
+// ---- fused multi-tensor AdamW (the reference steps torch.optim.AdamW over the decoder
+// and depth-encoder parameters, depth_train.py:136-137,221).  One launch for up to kMaxOptTensors
+// tensors (blockIdx.y = tensor); decoupled weight decay, bias-corrected moments, no amsgrad:
+//   p *= 1 - lr*wd ;  m += (g - m)(1 - b1) ;  v = b2 v + (1 - b2) g^2 ;
+//   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+constexpr int kMaxOptTensors = 32;
+struct AdamWJobs {
+  float* p[kMaxOptTensors];
+  const float* g[kMaxOptTensors];
+  float* m[kMaxOptTensors];
+  float* v[kMaxOptTensors];
+  long long n[kMaxOptTensors];
+  int count;
+  float lr_wd;        // lr * weight_decay
+  float one_m_b1, b2, one_m_b2;
+  float step_size;    // lr / (1 - b1^t)
+  float inv_sqrt_bc2; // 1 / sqrt(1 - b2^t)
+  float eps;
+};
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamWJobs a) {
+  const int j = blockIdx.y;
+  float* __restrict__ p = a.p[j];
+  const float* __restrict__ g = a.g[j];
+  float* __restrict__ m = a.m[j];
+  float* __restrict__ v = a.v[j];
+  const long long n = a.n[j];
+  const long long stride = (long long)gridDim.x * 256;
+  const bool vec = (n % 4 == 0) && (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                                      reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0);
+  auto upd = [&](float& pw, float gw, float& mw, float& vw) {
+    pw *= 1.f - a.lr_wd;
+    mw += (gw - mw) * a.one_m_b1;
+    vw = vw * a.b2 + a.one_m_b2 * gw * gw;
+    const float denom = sqrtf(vw) * a.inv_sqrt_bc2 + a.eps;
+    pw -= a.step_size * (mw / denom);
+  };
+  if (vec) {
+    const long long n4 = n / 4;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+      float4 pw = reinterpret_cast<float4*>(p)[i];
+      const float4 gw = reinterpret_cast<const float4*>(g)[i];
+      float4 mw = reinterpret_cast<float4*>(m)[i];
+      float4 vw = reinterpret_cast<float4*>(v)[i];
+      upd(pw.x, gw.x, mw.x, vw.x); upd(pw.y, gw.y, mw.y, vw.y);
+      upd(pw.z, gw.z, mw.z, vw.z); upd(pw.w, gw.w, mw.w, vw.w);
+      reinterpret_cast<float4*>(p)[i] = pw;
+      reinterpret_cast<float4*>(m)[i] = mw;
+      reinterpret_cast<float4*>(v)[i] = vw;
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) upd(p[i], g[i], m[i], v[i]);
+  }
+}
+
 __global__ void __launch_bounds__(256) add_vec_kernel(const float* a, const float* b, float* dst, int n) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < n) dst[i] = a[i] + b[i];

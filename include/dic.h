@@ -236,6 +236,14 @@ void dic_set_substreams(int n);
 int dic_trace_start(void* buf, unsigned int capacity_records);
 int dic_trace_stop(unsigned int* count);
 
+/* Fused multi-tensor AdamW step (replaces torch.optim.AdamW.step of
+ * depth_train.py:136-137,221 for fp32 CUDA tensors): decoupled weight decay, bias-corrected
+ * moments, no amsgrad.  n tensors; params / grads / exp_avg / exp_avg_sq are HOST arrays of n
+ * device pointers, sizes[i] = element count; step counts from 1. */
+int dic_adamw_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const long long* sizes, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* Test hook of the fused dL/dF GEMM (bf16 mode, csrc/dfeat_tc.cuh):
  *   dF[b] (L x D, bf16) = datt1[b] (L x A) . w_enc (A x D) + alpha16[b]^T (L x T) . dz[b] (T x D) + dmeanF[b] / L
  * datt1 [B*L, A] bf16; w_enc [A, D] bf16; alpha16 [B*T, Lp] bf16 (Lp % 8 == 0, columns >= L zero);

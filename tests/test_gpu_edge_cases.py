@@ -151,3 +151,28 @@ def test_flat_grad_buffer_aliases_param_grads(cuda_device):
     for (k, p), (_, q) in zip(got.named_parameters(), ref.named_parameters()):
         assert lo <= p.grad.data_ptr() < hi, k
         assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7 + 1e-5 * float(q.grad.abs().max())), k
+
+
+def test_fused_adamw_matches_torch(cuda_device):
+    """dic_adamw_step == torch.optim.AdamW over several steps (fp32 rounding), odd sizes included."""
+    torch.manual_seed(0)
+    shapes = [(128, 2048), (10000, 128), (513,), (1,), (7, 3), (2048,)]
+    ref = [torch.nn.Parameter(torch.randn(s, device=cuda_device)) for s in shapes]
+    got = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=1e-3, weight_decay=1e-2)
+    o_got = P.FusedAdamW(got, lr=1e-3, weight_decay=1e-2)
+    for step in range(5):
+        for a, b in zip(ref, got):
+            g = torch.randn_like(a) * (10.0 ** (step - 2))
+            a.grad = g.clone()
+            b.grad = g.clone()
+        o_ref.step()
+        o_got.step()
+    for a, b in zip(ref, got):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (a - b).abs().max()
+    sd = o_got.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    cpu_p = torch.nn.Parameter(torch.zeros(3))
+    cpu_p.grad = torch.ones(3)
+    with pytest.raises(P.DicError):          # no CPU fallback
+        P.FusedAdamW([cpu_p]).step()
