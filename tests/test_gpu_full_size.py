@@ -1,0 +1,144 @@
+"""BASELINE.json full-size configurations (batch 256 x 20 steps training, 128 images x 5 beams decoding,
+L=196, D=2048, A=E=H=128, V=10000) checked through size-independent properties -- the CPU oracle takes
+minutes at these sizes, so parity proper is in test_gpu_parity.py at sizes it finishes in seconds:
+  * attention weights are a distribution; padded steps of ragged captions stay zero
+  * images are independent: a batch gives the same logits / tokens as its two halves run separately
+  * the fused loss equals the unfused expression on the returned logits; gradients are linear in the
+    upstream gradient
+  * beam search: scores sorted per image and step, backpointers in range, finished hypotheses frozen,
+    lengths = position of the first <end>, beam = 1 equals greedy decoding
+"""
+import numpy as np
+import pytest
+import torch
+
+import depth_image_captioning_pub_b200 as P
+from oracle import decoder_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+L, D, A, E, H, V, T = 196, 2048, 128, 128, 128, 10000, 20
+
+
+def build(dev, precision, cls=P.CD_RNNDecoderWithSoftAttention, seed=1234):
+    m = cls(A, E, D, H, V)
+    m.load_state_dict(O.make_weights(A, E, D, H, V, seed=seed))
+    m.precision = precision
+    return m.to(dev).eval()
+
+
+def batch(B, seed, dtype, ragged=False):
+    g = torch.Generator().manual_seed(seed)
+    F_rgb = torch.rand(B, L, D, generator=g).to(dtype)
+    F_dep = torch.rand(B, L, D, generator=g).to(dtype)
+    lengths = sorted((torch.randint(8, T + 2, (B,), generator=g).tolist() if ragged else [T + 1] * B), reverse=True)
+    caps = torch.full((B, T + 1), V - 1, dtype=torch.int64)
+    for b, n in enumerate(lengths):
+        caps[b, 0] = V - 4
+        caps[b, 1:n - 1] = torch.randint(0, V - 4, (n - 2,), generator=g)
+        caps[b, n - 1] = V - 3
+    return F_rgb, F_dep, caps, lengths
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_train_step_full_size_properties(ragged, cuda_device):
+    dev = cuda_device
+    B = 256
+    F_rgb, F_dep, caps, lengths = batch(B, 11, torch.bfloat16, ragged)
+    m = build(dev, "bf16")
+    fr, fd, cp = F_rgb.to(dev), F_dep.to(dev).requires_grad_(True), caps.to(dev)
+    out, alphas = m(fr, fd, cp, lengths)
+    logits = out.data.float()
+    assert torch.isfinite(logits).all() and torch.isfinite(alphas).all()
+    assert out.batch_sizes.tolist() == [sum(1 for n in lengths if n - 1 > t) for t in range(max(lengths) - 1)]
+    # alpha: a distribution over the 196 regions for active steps, exactly zero for padded steps
+    s = alphas.sum(dim=2).cpu()
+    for b in (0, B // 2, B - 1):
+        n = lengths[b] - 1
+        assert torch.allclose(s[b, :n], torch.ones(n), atol=2e-3)
+        assert (alphas[b, n:] == 0).all()
+    assert (alphas >= 0).all()
+
+    # images are independent: the second half of the batch, run alone, gives the same logits
+    half = B // 2
+    out2, alphas2 = m(fr[half:].contiguous(), fd[half:].detach().contiguous(), cp[half:].contiguous(), lengths[half:])
+    sizes = out.batch_sizes.tolist()
+    sizes2 = out2.batch_sizes.tolist()
+    off = off2 = 0
+    worst = 0.0
+    for t, n2 in enumerate(sizes2):
+        n = sizes[t]
+        a = logits[off + half: off + half + n2] if n > half else None
+        if a is not None:
+            b_ = out2.data[off2: off2 + n2].float()
+            worst = max(worst, float((a[:b_.shape[0]] - b_).abs().max()))
+        off += n
+        off2 += n2
+    assert worst <= 2e-2 * float(logits.abs().max()), worst        # bf16 mode bound on the logits
+    assert float((alphas[half:, : alphas2.shape[1]] - alphas2).abs().max()) <= 2e-3
+
+    # fused loss == unfused expression; gradients linear in the upstream gradient
+    tg = O.pack_targets(caps, lengths).to(dev)
+    ref = torch.nn.functional.cross_entropy(out.data, tg, ignore_index=V - 1) + 0.7 * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+    g1 = {}
+    for scale in (1.0, 2.0):
+        m.zero_grad(set_to_none=True)
+        fd.grad = None
+        loss = m.forward_loss(fr, fd, cp, lengths, ignore_index=V - 1, lam=0.7)
+        assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-4 * max(1.0, abs(float(ref.detach())))
+        (loss * scale).backward()
+        cur = {k: p.grad.clone() for k, p in m.named_parameters()}
+        cur["dF"] = fd.grad.float().clone()
+        if scale == 1.0:
+            g1 = cur
+        else:
+            for k in cur:
+                assert torch.isfinite(cur[k]).all(), k
+                den = float(g1[k].abs().max()) + 1e-12
+                assert float((cur[k] - 2.0 * g1[k]).abs().max()) <= 2e-2 * den + 1e-9, k
+
+
+def test_beam_full_size_properties(cuda_device):
+    dev = cuda_device
+    B, K = 128, 5
+    F_rgb, F_dep, _, _ = batch(B, 12, torch.bfloat16)
+    m = build(dev, "bf16")
+    voc = O.synthetic_vocab(V)
+    end = voc["<end>"]
+    fr, fd = F_rgb.to(dev), F_dep.to(dev)
+    res = m.beam_search(fr, fd, voc, beam=K, max_length=T, trace=True)
+    tokens, lengths, scores = res["tokens"].cpu(), res["lengths"].cpu(), res["scores"].cpu()
+    back, toks, all_scores = res["back"].cpu(), res["toks"].cpu(), res["all_scores"].cpu()
+    assert tokens.shape == (B, T) and ((tokens >= 0) & (tokens < V)).all()
+    assert ((back >= 0) & (back < K)).all() and ((toks >= 0) & (toks < V)).all()
+    # stable top-k output is sorted: scores non-increasing along the beam axis, at every step
+    assert (all_scores[:, :, :-1] >= all_scores[:, :, 1:]).all()
+    assert torch.equal(scores, all_scores[-1, :, 0])
+    # cumulative log-probabilities never increase along a hypothesis; finished hypotheses are frozen
+    for t in range(1, T):
+        parent = torch.gather(all_scores[t - 1], 1, back[t].long())
+        assert (all_scores[t] <= parent + 1e-5).all()
+        prev_tok = torch.gather(toks[t - 1], 1, back[t].long())
+        frozen = prev_tok == end
+        assert (toks[t][frozen] == end).all()
+        assert torch.equal(all_scores[t][frozen], parent[frozen])
+    # lengths = position of the first <end> (or T)
+    for b in range(B):
+        row = tokens[b].tolist()
+        assert int(lengths[b]) == (row.index(end) + 1 if end in row else T)
+
+    # the best hypothesis is the backtrack of row 0
+    b = 7
+    row, seq = 0, []
+    for t in range(T - 1, -1, -1):
+        seq.append(int(toks[t, b, row]))
+        row = int(back[t, b, row])
+    assert seq[::-1] == tokens[b].tolist()
+
+    # beam = 1 is greedy decoding; images are independent (a half batch decodes to the same tokens)
+    greedy = torch.from_numpy(m.batch_sample(fr, fd, voc, max_length=T))
+    b1 = m.beam_search(fr, fd, voc, beam=1, max_length=T)["tokens"].cpu()
+    assert (greedy == b1).float().mean() >= 0.995       # identical up to last-ulp ties between GEMM tilings
+    halfres = m.beam_search(fr[64:].contiguous(), fd[64:].contiguous(), voc, beam=K, max_length=T)
+    assert (halfres["tokens"].cpu() == tokens[64:]).float().mean() >= 0.99
+    assert float((halfres["scores"].cpu() - scores[64:]).abs().max()) <= 5e-2
