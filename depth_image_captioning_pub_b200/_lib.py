@@ -71,7 +71,9 @@ PROTOTYPES = {
     "dic_decoder_backward_ex": (_I, [_DP, _I, _I, _P, _P, _P, _I, _P, _I, _IP, _I, _I, _P, _I, _P, _P, _F, _P,
                                      _PP, _P, _P, _SZ, _P]),
     "dic_caption_loss_workspace_bytes": (_SZ, [_I, _I]),
-    "dic_caption_loss": (_I, [_DP, _I, _P, _P, _I, _IP, _I, _I, _I, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "dic_caption_loss": (_I, [_DP, _I, _P, _I, _P, _I, _IP, _I, _I, _I, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "dic_decoder_forward_ex": (_I, [_DP, _I, _I, _P, _P, _P, _I, _P, _I, _IP, _I, _I, _P, _F, _P, _P, _I, _P, _P,
+                                    _SZ, _P]),
     "dic_scale_loss_grads": (_I, [_I, _P, _P, _SZ, _P, _SZ, _P]),
     "dic_decode_workspace_bytes": (_SZ, [_DP, _I, _I, _I]),
     "dic_decode_greedy": (_I, [_DP, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),

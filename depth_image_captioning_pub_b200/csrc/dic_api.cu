@@ -178,7 +178,8 @@ template <typename ST>
 static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pack, const void* f_rgb,
                                 const void* f_depth, int feat_dtype, const int64_t* captions,
                                 int cap_stride, const StepSizes& sizes, int total, int T, int B,
-                                const float* u, float temp, const float* dropout_mask, float* logits,
+                                const float* u, float temp, const float* dropout_mask, void* logits,
+                                int logits_bf16,
                                 float* alphas, char* ws, cudaStream_t st) {
   const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
   const int is_bf16 = sizeof(ST) == 2;
@@ -287,8 +288,8 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
 
   // logits for every packed row at once: linear(dropout(h)) (depth_models.py:197), written in
   // PackedSequence (time-major) order
-  GemmArgs g = gemm_args_nt(Hdrop, is_bf16, d.H, pk.Wout(), is_bf16, d.H, logits, 0, d.V, total, d.V, d.H,
-                            pk.b_out());
+  GemmArgs g = gemm_args_nt(Hdrop, is_bf16, d.H, pk.Wout(), is_bf16, d.H, logits, logits_bf16, d.V, total, d.V,
+                            d.H, pk.b_out());
   DIC_TRY(gemm(g, st));
   return 0;
 }
@@ -844,17 +845,19 @@ size_t dic_train_workspace_bytes(const dic_dims* dims, int dtype, int B, int T) 
   return TrainLayout(*dims, dtype, B, T).bytes;
 }
 
-int dic_decoder_forward(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
-                        const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
-                        const int32_t* host_batch_sizes, int T, int B, const float* u, float temp,
-                        const float* dropout_mask, float* logits, float* alphas, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+int dic_decoder_forward_ex(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
+                           const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
+                           const int32_t* host_batch_sizes, int T, int B, const float* u, float temp,
+                           const float* dropout_mask, void* logits, int logits_dtype, float* alphas,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   DIC_TRY(check_dims(dims, dtype));
   if (!pack || !f_rgb || !captions || !host_batch_sizes || !logits || !alphas || !workspace)
     DIC_FAIL(-1, "null argument");
   if (attn_mode < 0 || attn_mode > 2) DIC_FAIL(-1, "bad attn_mode %d", attn_mode);
   if (attn_mode != DIC_ATTN_SOFT && !u) DIC_FAIL(-1, "hard attention needs the uniform draws u");
   if (attn_mode == DIC_ATTN_GUMBEL_SOFTMAX && !(temp > 0.f)) DIC_FAIL(-1, "temp must be > 0");
+  if (logits_dtype != DIC_F32 && !(logits_dtype == DIC_BF16 && dtype == DIC_BF16))
+    DIC_FAIL(-1, "logits are float32, or bfloat16 in bf16 mode");
   StepSizes sizes;
   int total = 0;
   DIC_TRY(make_sizes(host_batch_sizes, T, B, &sizes, &total));
@@ -864,11 +867,22 @@ int dic_decoder_forward(const dic_dims* dims, int dtype, int attn_mode, const vo
   if (workspace_bytes < need) DIC_FAIL(-1, "workspace too small: %zu < %zu", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   char* ws = reinterpret_cast<char*>(workspace);
+  const int lb = logits_dtype == DIC_BF16;
   if (dtype == DIC_BF16)
     return decoder_forward_impl<bf16>(*dims, attn_mode, pack, f_rgb, f_depth, feat_dtype, captions, cap_stride,
-                                      sizes, total, T, B, u, temp, dropout_mask, logits, alphas, ws, st);
+                                      sizes, total, T, B, u, temp, dropout_mask, logits, lb, alphas, ws, st);
   return decoder_forward_impl<float>(*dims, attn_mode, pack, f_rgb, f_depth, feat_dtype, captions, cap_stride,
-                                     sizes, total, T, B, u, temp, dropout_mask, logits, alphas, ws, st);
+                                     sizes, total, T, B, u, temp, dropout_mask, logits, lb, alphas, ws, st);
+}
+
+int dic_decoder_forward(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
+                        const void* f_depth, int feat_dtype, const int64_t* captions, int cap_stride,
+                        const int32_t* host_batch_sizes, int T, int B, const float* u, float temp,
+                        const float* dropout_mask, float* logits, float* alphas, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return dic_decoder_forward_ex(dims, dtype, attn_mode, pack, f_rgb, f_depth, feat_dtype, captions, cap_stride,
+                                host_batch_sizes, T, B, u, temp, dropout_mask, logits, DIC_F32, alphas, workspace,
+                                workspace_bytes, stream);
 }
 
 int dic_decoder_backward_ex(const dic_dims* dims, int dtype, int attn_mode, const void* pack, const void* f_rgb,
@@ -922,9 +936,9 @@ size_t dic_caption_loss_workspace_bytes(int N, int B) {
   return loss_workspace_bytes(N, B);
 }
 
-int dic_caption_loss(const dic_dims* dims, int dtype, const float* logits, const int64_t* captions, int cap_stride,
-                     const int32_t* host_batch_sizes, int T, int B, int ignore_index, const float* alphas,
-                     float lam, float* loss, void* d_logits, float* d_alphas, void* workspace,
+int dic_caption_loss(const dic_dims* dims, int dtype, const void* logits, int logits_dtype, const int64_t* captions,
+                     int cap_stride, const int32_t* host_batch_sizes, int T, int B, int ignore_index,
+                     const float* alphas, float lam, float* loss, void* d_logits, float* d_alphas, void* workspace,
                      size_t workspace_bytes, void* stream) {
   DIC_TRY(check_dims(dims, dtype));
   if (!logits || !captions || !host_batch_sizes || !loss || !d_logits || !workspace) DIC_FAIL(-1, "null argument");
@@ -933,11 +947,12 @@ int dic_caption_loss(const dic_dims* dims, int dtype, const float* logits, const
   DIC_TRY(make_sizes(host_batch_sizes, T, B, &sizes, &total));
   if (T + 1 > cap_stride) DIC_FAIL(-1, "captions has %d columns, need >= T+1 = %d", cap_stride, T + 1);
   if (workspace_bytes < loss_workspace_bytes(total, B)) DIC_FAIL(-1, "workspace too small");
-  if (dtype == DIC_BF16 && reinterpret_cast<const void*>(logits) == d_logits)
-    DIC_FAIL(-1, "bf16 d_logits cannot alias the fp32 logits");
+  if (logits_dtype != DIC_F32 && !(logits_dtype == DIC_BF16 && dtype == DIC_BF16))
+    DIC_FAIL(-1, "logits are float32, or bfloat16 in bf16 mode");
+  if (logits == d_logits && logits_dtype != dtype) DIC_FAIL(-1, "in-place d_logits needs logits in the storage dtype");
   LossArgs p;
   memset(&p, 0, sizeof(p));
-  p.logits = logits; p.captions = captions; p.cap_stride = cap_stride; p.sizes = sizes;
+  p.logits = logits; p.logits_bf16 = logits_dtype == DIC_BF16; p.captions = captions; p.cap_stride = cap_stride; p.sizes = sizes;
   p.T = T; p.B = B; p.N = total; p.V = dims->V; p.L = dims->L; p.ignore_index = ignore_index;
   p.alphas = alphas; p.lam = lam; p.loss = loss; p.d_logits = d_logits; p.d_alphas = d_alphas;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -107,19 +107,19 @@ class Engine:
 
     # ---- raw calls ---------------------------------------------------------------------------
     def forward(self, attn_mode: int, f_rgb, f_depth, captions, batch_sizes: Sequence[int], u, temp: float,
-                dropout_mask, ws) -> Tuple[torch.Tensor, torch.Tensor]:
+                dropout_mask, ws, logits_dtype=torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
         d = self.dims
         B, T = f_rgb.shape[0], len(batch_sizes)
         total = int(sum(batch_sizes))
-        logits = torch.empty(total, d.V, dtype=torch.float32, device=self.device)
+        logits = torch.empty(total, d.V, dtype=logits_dtype, device=self.device)
         alphas = torch.zeros(B, T, d.L, dtype=torch.float32, device=self.device)
         bs = (C.c_int32 * T)(*batch_sizes)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.dic_decoder_forward(
+            _lib.check(self.lib.dic_decoder_forward_ex(
                 C.byref(d), self.dtype, attn_mode, _lib.ptr(self.pack), _lib.ptr(f_rgb), _lib.ptr(f_depth),
                 _lib.dtype_code(f_rgb), _lib.ptr(captions), captions.shape[1], bs, T, B, _lib.ptr(u),
-                float(temp), _lib.ptr(dropout_mask), _lib.ptr(logits), _lib.ptr(alphas), _lib.ptr(ws),
-                ws.numel(), _lib.stream_ptr(self.device)))
+                float(temp), _lib.ptr(dropout_mask), _lib.ptr(logits), _lib.dtype_code(logits), _lib.ptr(alphas),
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)))
         return logits, alphas
 
     def backward(self, attn_mode: int, f_rgb, f_depth, captions, batch_sizes, d_logits, d_alphas, alphas,
@@ -166,10 +166,10 @@ class Engine:
         B, T = captions.shape[0], len(batch_sizes)
         N = int(sum(batch_sizes))
         loss = torch.empty(1, dtype=torch.float32, device=self.device)
-        if self.dtype == _lib.DIC_BF16:
-            d_logits = torch.empty(N, d.V, dtype=torch.bfloat16, device=self.device)
+        if _lib.dtype_code(logits) == self.dtype:
+            d_logits = logits          # same dtype (fp32 mode, or bf16 logits in bf16 mode): in place
         else:
-            d_logits = logits          # fp32 mode: in place
+            d_logits = torch.empty(N, d.V, dtype=torch.bfloat16, device=self.device)
         use_reg = alphas is not None and lam != 0.0
         d_alphas = torch.empty_like(alphas) if use_reg else None
         n = self.lib.dic_caption_loss_workspace_bytes(N, B)
@@ -177,7 +177,8 @@ class Engine:
         bs = (C.c_int32 * T)(*batch_sizes)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dic_caption_loss(
-                C.byref(d), self.dtype, _lib.ptr(logits), _lib.ptr(captions), captions.shape[1], bs, T, B,
+                C.byref(d), self.dtype, _lib.ptr(logits), _lib.dtype_code(logits), _lib.ptr(captions),
+                captions.shape[1], bs, T, B,
                 int(ignore_index), _lib.ptr(alphas) if use_reg else None, float(lam), _lib.ptr(loss),
                 _lib.ptr(d_logits), _lib.ptr(d_alphas), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)))
         return loss, d_logits, d_alphas
@@ -305,8 +306,11 @@ class CaptionLossFunction(torch.autograd.Function):
             or (f_depth is not None and f_depth.requires_grad))
         engine.ensure_packed(params)
         ws = engine.train_workspace(f_rgb.shape[0], len(batch_sizes), fresh=needs_grad)
+        # bf16 mode keeps the [sum(bs), V] logits block in bf16 (within the mode's 2e-2 bound on the logits):
+        # the loss head overwrites it with d_logits in place
+        ldt = torch.bfloat16 if engine.dtype == _lib.DIC_BF16 else torch.float32
         logits, alphas = engine.forward(attn_mode, f_rgb, f_depth, captions, batch_sizes, u, temp,
-                                        dropout_mask, ws)
+                                        dropout_mask, ws, logits_dtype=ldt)
         loss, d_logits, d_alphas = engine.caption_loss(logits, captions, batch_sizes, ignore_index,
                                                        alphas if lam != 0.0 else None, lam)
         ctx.engine, ctx.attn_mode, ctx.batch_sizes, ctx.temp = engine, attn_mode, list(batch_sizes), temp

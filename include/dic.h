@@ -134,6 +134,16 @@ int dic_decoder_backward(const dic_dims* dims, int dtype, int attn_mode, const v
                          const dic_params* grads, void* d_feats, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Same as dic_decoder_forward, with the logits written as float32 or, in bf16 mode, bfloat16
+ * (logits_dtype): the fused training step keeps them in bf16 and the loss head overwrites them
+ * with d_logits in place, which halves the traffic of the [sum(bs), V] block. */
+int dic_decoder_forward_ex(const dic_dims* dims, int dtype, int attn_mode, const void* pack,
+                           const void* f_rgb, const void* f_depth, int feat_dtype,
+                           const int64_t* captions, int cap_stride, const int32_t* host_batch_sizes,
+                           int T, int B, const float* u, float temp, const float* dropout_mask,
+                           void* logits, int logits_dtype, float* alphas, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* Same as dic_decoder_backward, with d_logits in either float32 or the storage dtype of the mode
  * (d_logits_dtype = DIC_F32 / DIC_BF16): the fused loss head below writes bf16 d_logits directly,
  * which saves the fp32 -> bf16 operand copy of the tensor-core GEMMs. */
@@ -150,14 +160,16 @@ int dic_decoder_backward_ex(const dic_dims* dims, int dtype, int attn_mode, cons
  *   loss = cross_entropy(packed logits, packed targets, ignore_index, mean over non-ignored)
  *        + lam * mean_{b,l} (1 - sum_t alphas[b,t,l])^2       (lam = 0 / alphas NULL: CE only)
  * and returns its gradients for an upstream gradient of 1: d_logits [N,V] in the storage dtype
- * of the mode (fp32 mode: may alias `logits`), d_alphas [B,T,L] fp32 (may be NULL).
+ * of the mode (may alias `logits` when those have the same dtype), d_alphas [B,T,L] fp32 (may
+ * be NULL).  logits: float32, or (bf16 mode, dic_decoder_forward_ex) bfloat16.
  * Targets are read from `captions` (target of packed row (t,b) = captions[b,t+1]).
  * loss: [1] fp32 on the device.  No host synchronisation. */
 size_t dic_caption_loss_workspace_bytes(int N, int B);
-int dic_caption_loss(const dic_dims* dims, int dtype, const float* logits, const int64_t* captions,
-                     int cap_stride, const int32_t* host_batch_sizes, int T, int B,
-                     int ignore_index, const float* alphas, float lam, float* loss, void* d_logits,
-                     float* d_alphas, void* workspace, size_t workspace_bytes, void* stream);
+int dic_caption_loss(const dic_dims* dims, int dtype, const void* logits, int logits_dtype,
+                     const int64_t* captions, int cap_stride, const int32_t* host_batch_sizes, int T,
+                     int B, int ignore_index, const float* alphas, float lam, float* loss,
+                     void* d_logits, float* d_alphas, void* workspace, size_t workspace_bytes,
+                     void* stream);
 /* d_logits, d_alphas *= grad_loss[0] (device scalar); a no-op kernel when it is exactly 1. */
 int dic_scale_loss_grads(int dtype, const float* grad_loss, void* d_logits, size_t n_logits,
                          float* d_alphas, size_t n_alphas, void* stream);

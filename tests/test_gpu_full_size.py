@@ -85,7 +85,8 @@ def test_train_step_full_size_properties(ragged, cuda_device):
         m.zero_grad(set_to_none=True)
         fd.grad = None
         loss = m.forward_loss(fr, fd, cp, lengths, ignore_index=V - 1, lam=0.7)
-        assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-4 * max(1.0, abs(float(ref.detach())))
+        # (bf16 logits inside the fused step: 2^-9 relative rounding per logit)
+        assert abs(float(loss.detach()) - float(ref.detach())) <= 2e-3 * max(1.0, abs(float(ref.detach())))
         (loss * scale).backward()
         cur = {k: p.grad.clone() for k, p in m.named_parameters()}
         cur["dF"] = fd.grad.float().clone()

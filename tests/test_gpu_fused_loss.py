@@ -71,7 +71,10 @@ def test_forward_loss_matches_unfused(case, precision, cuda_device):
     for scale in (1.0, 3.0):
         l_ref, g_ref = run(False, scale)
         l_fus, g_fus = run(True, scale)
-        assert abs(l_ref - l_fus) <= 2e-6 * max(1.0, abs(l_ref))
+        # bf16 mode: the fused step keeps the logits block in bf16 (2^-9 relative rounding per logit, inside
+        # the mode's 2e-2 bound), so its loss differs from the loss on the fp32 copy of the same logits
+        ltol = 2e-6 if precision == "fp32" else 2e-3
+        assert abs(l_ref - l_fus) <= ltol * max(1.0, abs(l_ref))
         # bf16 mode: d_logits is rounded to bf16 either way (same values), fp32: identical math up to
         # the reduction order of the log-sum-exp
         tol = 2e-5 if precision == "fp32" else 2e-2
