@@ -350,6 +350,34 @@ def run_b200(args):
         ms_g = timed(lambda: m.batch_sample(fr, fd, voc, max_length=T), args.steps)
         extra["greedy_captions_per_s"] = Bd * world * args.steps / (ms_g * 1e-3)
         m.train()
+        # ---- BASELINE.json configs[3]: depth-hard (Gumbel) variants, 256 captions --------------------------
+        # (the uniform draws come from the CPU generator exactly like the reference, attention.py:17,40,
+        # so these numbers include the host RNG and its H2D copy)
+        mh = P.CD_RNNDecoderWithHardAttention(A, E, D, H, V, str(dev))
+        mh.load_state_dict(m.state_dict())
+        mh.precision = args.precision
+        mh = mh.to(dev).train()
+        oh = P.FusedAdamW(list(mh.parameters()), lr=1e-3)
+
+        def hard_step():
+            loss = mh.forward_loss(F_rgb, F_dep, caps, lengths, torch.tensor(1.0), ignore_index=V - 1)
+            loss.backward()
+            oh.step()
+            oh.zero_grad(set_to_none=True)
+            F_dep.grad = None
+        for _ in range(2):
+            hard_step()
+        hs = max(4, args.steps // 4)
+        ms_h = timed(hard_step, hs)
+        extra["hard_train_tokens_per_s"] = B * T * world * hs / (ms_h * 1e-3)
+        mh.eval()
+        mh.cache_packed_weights = True
+        for _ in range(2):
+            mh.batch_sample(F_rgb, F_dep.detach(), voc, max_length=T)
+        ms_hg = timed(lambda: mh.batch_sample(F_rgb, F_dep.detach(), voc, max_length=T), hs)
+        extra["hard_greedy_captions_per_s"] = B * world * hs / (ms_hg * 1e-3)
+        extra["hard_config"] = {"images_per_gpu": B, "max_len": T, "temp": 1.0,
+                                "noise": "torch.rand on the CPU generator per call + H2D (reference semantics)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
