@@ -372,11 +372,14 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
 
 template <typename ST, int KB>
 inline int launch_attn_context_bulk(const AttnFwdArgs& p, int images, cudaStream_t st);   // attention_bulk.cuh
-inline bool bulk_ctx_enabled() {
+template <typename ST, int KB>
+inline int launch_attn_context_mma_st(const AttnFwdArgs& p, int images, cudaStream_t st);  // attention_mma.cuh
+inline int bulk_ctx_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DIC_BULK_CTX"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("DIC_BULK_CTX"); v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
+  return v;
 }
+inline bool bulk_ctx_enabled() { return bulk_ctx_mode() != 0; }
 
 template <typename ST, int KB>
 inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st) {
@@ -411,7 +414,13 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
     DIC_LAUNCH_CHECK();
   }
   if (KB >= 3 && p.mode == DIC_ATTN_SOFT && bulk_ctx_enabled()) {
-    // several beams per image: bulk-copy / shared-memory staged variant (attention_bulk.cuh)
+    // several beams per image: tensor-core variant for bf16 storage (attention_mma.cuh), TMA-staged FP32
+    // variant otherwise (attention_bulk.cuh).  DIC_BULK_CTX=0 falls back to the register-streaming kernel,
+    // DIC_BULK_CTX=2 forces the FP32 staged variant.
+    // measured at 128 images (profiles/r01_beam_ctx_variants.txt): 3 beams 19.7 us staged FP32 vs 21.9 us MMA,
+    // 5 beams 24.9 vs 24.1, 8 beams 31.5 vs 24.0 (the MMA variant does not depend on the beam count)
+    if (sizeof(ST) == 2 && KB >= 4 && p.D % 8 == 0 && !p.z_out && bulk_ctx_mode() == 1)
+      return launch_attn_context_mma_st<ST, KB>(p, images, st);
     return launch_attn_context_bulk<ST, KB>(p, images, st);
   }
   {

@@ -2,6 +2,7 @@
 // One translation unit: kernels are header templates, this file instantiates and sequences them.
 #include "attention.cuh"
 #include "attention_bulk.cuh"
+#include "attention_mma.cuh"
 #include "common.cuh"
 #include "decode.cuh"
 #include "dfeat_tc.cuh"

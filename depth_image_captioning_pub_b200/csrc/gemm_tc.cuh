@@ -490,7 +490,7 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with row stride ld (elements);
 // box = [box_rows, 64 cols] (64 bf16 = 128 bytes), 128B swizzle, zero fill out of bounds.
 inline int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
-                          int box_rows) {
+                          int box_rows, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) DIC_FAIL(-6, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -498,7 +498,7 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long
   cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) DIC_FAIL(-6, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return 0;

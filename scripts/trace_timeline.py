@@ -16,6 +16,7 @@ ap.add_argument("what", nargs="?", default="train")
 ap.add_argument("--sub", type=int, default=1)
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--rows", type=int, default=70)
+ap.add_argument("--beam", type=int, default=5)
 ap.add_argument("--skip", type=int, default=0, help="launches to skip before printing")
 ap.add_argument("--detail", type=int, default=-1, help="kernel id: per-CTA go/exit distribution of one launch")
 args = ap.parse_args()
@@ -48,7 +49,7 @@ else:
     m.eval(); m.cache_packed_weights = True
     Bd = min(B, 128) if args.batch == 256 else B
     fr, fd = F_rgb[:Bd].contiguous(), F_dep[:Bd].detach().contiguous()
-    fn = (lambda: m.beam_search(fr, fd, voc, beam=5, max_length=T)) if args.what == "beam" else \
+    fn = (lambda: m.beam_search(fr, fd, voc, beam=args.beam, max_length=T)) if args.what == "beam" else \
          (lambda: m.batch_sample(fr, fd, voc, max_length=T))
 for _ in range(3):
     fn()
