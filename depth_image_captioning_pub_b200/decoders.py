@@ -142,8 +142,13 @@ class _DecoderBase(nn.Module):
 
     def _draw_u(self, rows: int, L: int, device) -> torch.Tensor:
         # one draw for all steps == the reference's per-step torch.rand(bs_valid, k) calls on the
-        # CPU generator concatenated (attention.py:17,40)
-        return torch.rand(rows, L).to(device)
+        # CPU generator concatenated (attention.py:17,40).  Drawn into pinned memory and copied without a
+        # host synchronisation, so the host RNG of step n+1 overlaps the device work of step n.
+        if not torch.cuda.is_available():
+            return torch.rand(rows, L).to(device)
+        host = torch.empty(rows, L, dtype=torch.float32, pin_memory=True)
+        torch.rand(rows, L, out=host)
+        return host.to(device, non_blocking=True)
 
     @torch.no_grad()
     def _greedy(self, attn_mode, features, depth_features, word_to_id, max_length, want_alphas):
