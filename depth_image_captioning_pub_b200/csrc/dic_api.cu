@@ -8,6 +8,7 @@
 #include "dfeat_tc.cuh"
 #include "gemm_generic.cuh"
 #include "gemm_tc.cuh"
+#include "gates_lstm.cuh"
 #include "layout.cuh"
 #include "loss.cuh"
 #include "lstm.cuh"
@@ -160,6 +161,24 @@ static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long 
   return gemm(g, st);
 }
 
+// one LSTM step: cluster-fused GEMM + pointwise (bf16 mode, gates_lstm.cuh) or split-K GEMM + lstm kernel
+template <typename ST>
+static int lstm_step(const dic_dims& d, const Pack& pk, const ST* X, long long XW, int rows, int rows_alloc,
+                     float* gate_part, LstmFwdArgs l, cudaStream_t st) {
+  if constexpr (sizeof(ST) == 2) {
+    // one wave of 8-CTA clusters only: with more tiles than that the split-K GEMM spreads the work better
+    if (gates_lstm_eligible(d.H, (int)XW, X, XW) && cdiv(rows, kTcBM) * (4 * d.H / kGlBN) * kGlSplits <= tc_num_sms())
+      return launch_gates_lstm(reinterpret_cast<const bf16*>(X), XW, reinterpret_cast<const bf16*>(pk.Wgp()), rows,
+                               d.H, (int)XW, l, st);
+  }
+  int splits = 1;
+  DIC_TRY(gates_gemm<ST>(d, pk, X, XW, rows, rows_alloc, gate_part, &splits, st));
+  l.gate_part = gate_part;
+  l.part_stride = (long long)rows_alloc * 4 * d.H;
+  l.splits = splits;
+  return launch_lstm_fwd<ST>(l, st);
+}
+
 // Number of sub-batch streams of a time loop.  Measured on B200 (scripts/sub_sweep.py, gpurun_out/sweep1.log):
 // 2 streams gain 1% on the training step and lose 10% on decode, more streams lose everywhere -- the
 // streaming kernels fill every SM's register file (8 CTAs x 64 regs x 128 threads), so another
@@ -267,13 +286,10 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
       a.inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
       DIC_TRY(launch_attn_step<ST>(a, n, 1, sst));
 
-      int splits = 1;
       float* gp = gate_part + (size_t)r0 * 4 * d.H;
-      DIC_TRY(gates_gemm<ST>(d, pk, X, (long long)XW, n, B, gp, &splits, sst));
 
       LstmFwdArgs l;
       memset(&l, 0, sizeof(l));
-      l.gate_part = gp; l.part_stride = (long long)B * 4 * d.H; l.splits = splits;
       l.bias_g = pk.bias_g();
       l.c_in = c_all + ((size_t)t * B + r0) * d.H;
       l.c_out = c_all + ((size_t)(t + 1) * B + r0) * d.H;
@@ -282,7 +298,7 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
       l.hdrop_out = Hdrop + (size_t)off * d.H;
       l.mask = dropout_mask ? dropout_mask + (size_t)off * d.H : nullptr;
       l.rows = n; l.H = d.H;
-      DIC_TRY(launch_lstm_fwd<ST>(l, sst));
+      DIC_TRY(lstm_step<ST>(d, pk, X, (long long)XW, n, B, gp, l, sst));
     }
   }
   DIC_TRY(sub_join(st, S));
@@ -647,20 +663,17 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       a.L = L; a.D = D; a.A = A; a.mode = attn_mode; a.inv_temp = 1.f;
       DIC_TRY(launch_attn_step<ST>(a, Bs, K, sst));
 
-      int splits = 1;
       float* gp = gate_part + r0 * 4 * H;
-      DIC_TRY(gates_gemm<ST>(d, pk, X, XW, Rs, R, gp, &splits, sst));
 
       LstmFwdArgs l;
       memset(&l, 0, sizeof(l));
-      l.gate_part = gp; l.part_stride = (long long)R * 4 * H; l.splits = splits;
       l.bias_g = pk.bias_g();
       l.c_in = c + r0 * H;
       l.c_out = beam ? c_tmp + r0 * H : c + r0 * H;
       l.h_out = beam ? h_tmp + r0 * H : Xn + E + D;
       l.h_stride = beam ? H : XW;
       l.rows = Rs; l.H = H;
-      DIC_TRY(launch_lstm_fwd<ST>(l, sst));
+      DIC_TRY(lstm_step<ST>(d, pk, X, XW, Rs, R, gp, l, sst));
 
       float* lg = logits_out ? logits_out + ((size_t)t * R + r0) * V : logits_ws + r0 * V;
       const ST* hsrc = beam ? h_tmp + r0 * H : Xn + E + D;
@@ -786,6 +799,8 @@ int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void*
     PackJob& j = jobs.j[jobs.n++];
     j.src = src; j.src2 = src2; j.dst = dst; j.src_ld = src_ld; j.dst_ld = dst_ld; j.R = R; j.C = C;
     j.dst_bf16 = dst_bf16;
+    j.gate_H = 0;
+    j.gate_U = 16;
   };
   add(p->enc_att_w, d.D, base + lay.Wenc, d.D, bf, d.A, d.D);
   add(p->w_hh, d.H, base + lay.Whdb, d.H, bf, 4 * d.H, d.H);
@@ -793,6 +808,12 @@ int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void*
   add(p->fbeta_w, d.H, base + lay.Whdb + (size_t)(4 * d.H + d.A) * d.H * es, d.H, bf, d.D, d.H);
   add(p->w_ih, d.E + d.D, base + lay.Wg, XW, bf, 4 * d.H, d.E + d.D);
   add(p->w_hh, d.H, base + lay.Wg + (size_t)(d.E + d.D) * es, XW, bf, 4 * d.H, d.H);
+  if (bf && d.H % kGlUnits == 0 && gates_lstm_enabled()) {     // gate-interleaved copy for the cluster-fused LSTM step
+    add(p->w_ih, d.E + d.D, base + lay.Wgp, XW, bf, 4 * d.H, d.E + d.D);
+    jobs.j[jobs.n - 1].gate_H = d.H; jobs.j[jobs.n - 1].gate_U = kGlUnits;
+    add(p->w_hh, d.H, base + lay.Wgp + (size_t)(d.E + d.D) * es, XW, bf, 4 * d.H, d.H);
+    jobs.j[jobs.n - 1].gate_H = d.H; jobs.j[jobs.n - 1].gate_U = kGlUnits;
+  }
   add(p->init_w, d.D, base + lay.Winit, d.D, bf, 2 * d.H, d.D);
   add(p->lin_w, d.H, base + lay.Wout, d.H, bf, d.V, d.H);
   add(p->embed_w, d.E, base + lay.Emb, d.E, bf, d.V, d.E);

@@ -19,11 +19,12 @@ struct Carver {
 //   Whdb  [4H+A+D, H]      rows: W_hh | W_dec | W_beta  (backward: dh = G . Whdb)
 //         Wdb = Whdb + 4H*H  -> [A+D, H] forward h-projection (att2 | beta)
 //   Wg    [4H, E+D+H]      [W_ih | W_hh]: gates = [emb|zg|h] . Wg^T
+//   Wgp   [4H, E+D+H]      Wg with rows interleaved per tile of U = 32 units: row (u/U)*4U + gate*U + u%U = Wg row gate*H + u
 //   Winit [2H,D], Wout [V,H], Emb [V,E]
 //   fp32: b_enc[A], bias_db[A+D] = b_dec|b_beta, bias_g[4H] = b_ih+b_hh, b_init[2H], b_out[V],
 //         w_full[A], b_full[1]
 struct PackLayout {
-  size_t Wenc, Whdb, Wg, Winit, Wout, Emb;
+  size_t Wenc, Whdb, Wg, Wgp, Winit, Wout, Emb;
   size_t b_enc, bias_db, bias_g, b_init, b_out, w_full, b_full;
   size_t bytes;
   int es;  // element size of ST
@@ -34,6 +35,7 @@ struct PackLayout {
     Wenc = c.take((size_t)d.A * d.D * es);
     Whdb = c.take((size_t)(4 * d.H + d.A + d.D) * d.H * es);
     Wg = c.take((size_t)4 * d.H * XW * es);
+    Wgp = c.take((size_t)4 * d.H * XW * es);   // gate-interleaved copy of Wg (gates_lstm.cuh)
     Winit = c.take((size_t)2 * d.H * d.D * es);
     Wout = c.take((size_t)d.V * d.H * es);
     Emb = c.take((size_t)d.V * d.E * es);
@@ -57,6 +59,7 @@ struct Pack {
   const void* Whdb() const { return base + lay.Whdb; }
   const void* Wdb(const dic_dims& d) const { return base + lay.Whdb + (size_t)4 * d.H * d.H * lay.es; }
   const void* Wg() const { return base + lay.Wg; }
+  const void* Wgp() const { return base + lay.Wgp; }
   const void* Winit() const { return base + lay.Winit; }
   const void* Wout() const { return base + lay.Wout; }
   const void* Emb() const { return base + lay.Emb; }

@@ -267,6 +267,8 @@ struct PackJob {
   void* dst;
   long long src_ld, dst_ld;
   int R, C, dst_bf16;
+  int gate_H;              // > 0: destination row of source row q*gate_H + u is (u/U)*4U + q*U + u%U, U = gate_U
+  int gate_U;
 };
 constexpr int kMaxPackJobs = 20;
 struct PackJobs {
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJobs jobs) {
   const PackJob& jb = jobs.j[blockIdx.y];
   const size_t n = (size_t)jb.R * jb.C;
   const bool dense = jb.src_ld == jb.C && jb.dst_ld == jb.C;
-  if (dense && jb.dst_bf16 && !jb.src2 && n % 8 == 0 &&
+  if (dense && jb.dst_bf16 && !jb.src2 && jb.gate_H == 0 && n % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(jb.src) | reinterpret_cast<uintptr_t>(jb.dst)) & 15) == 0) {
     const size_t n8 = n / 8;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
@@ -291,7 +293,12 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJobs jobs) {
     const size_t r = i / jb.C, c = i - r * jb.C;
     float v = jb.src[r * jb.src_ld + c];
     if (jb.src2) v += jb.src2[r * jb.src_ld + c];
-    st_from_float(jb.dst, r * jb.dst_ld + c, v, jb.dst_bf16);
+    size_t rd = r;
+    if (jb.gate_H > 0) {
+      const size_t q = r / jb.gate_H, u = r - q * jb.gate_H;
+      rd = (u / jb.gate_U) * 4 * jb.gate_U + q * jb.gate_U + (u % jb.gate_U);
+    }
+    st_from_float(jb.dst, rd * jb.dst_ld + c, v, jb.dst_bf16);
   }
 }
 

@@ -176,3 +176,38 @@ def test_fused_adamw_matches_torch(cuda_device):
     cpu_p.grad = torch.ones(3)
     with pytest.raises(P.DicError):          # no CPU fallback
         P.FusedAdamW([cpu_p]).step()
+
+
+def test_cluster_fused_lstm_step_matches_default_path(cuda_device):
+    """DIC_FUSED_GATES=1 (gates GEMM + split-K reduction over distributed shared memory + LSTM pointwise in
+    one cluster kernel, csrc/gates_lstm.cuh) gives the same logits / tokens as the default two-kernel path.
+    The switch is read once per process, so the fused run happens in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import depth_image_captioning_pub_b200 as P
+from oracle import decoder_oracle as O
+A, E, D, H, V, L, B, T = 128, 128, 2048, 128, 1000, 196, 130, 6
+m = P.CD_RNNDecoderWithSoftAttention(A, E, D, H, V); m.load_state_dict(O.make_weights(A, E, D, H, V, seed=5)); m.precision = "bf16"
+m = m.cuda().eval()
+g = torch.Generator().manual_seed(6)
+Fr, Fd = torch.rand(B, L, D, generator=g).cuda(), torch.rand(B, L, D, generator=g).cuda()
+caps = torch.randint(0, V - 4, (B, T + 1), generator=g).cuda(); caps[:, 0] = V - 4
+out, alphas = m(Fr, Fd, caps, [T + 1] * B)
+toks = m.batch_sample(Fr, Fd, O.synthetic_vocab(V), max_length=T)
+torch.save({"logits": out.data.float().cpu(), "alphas": alphas.cpu(), "toks": torch.from_numpy(toks)}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    res = {}
+    for flag in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, DIC_FUSED_GATES=flag)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            res[flag] = torch.load(f.name)
+    a, b = res["0"], res["1"]
+    assert float((a["logits"] - b["logits"]).abs().max()) <= 2e-2 * float(a["logits"].abs().max())
+    assert float((a["alphas"] - b["alphas"]).abs().max()) <= 2e-3
+    assert (a["toks"] == b["toks"]).float().mean() >= 0.98
