@@ -825,7 +825,7 @@ int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void*
   add(p->lin_b, d.V, base + lay.b_out, d.V, 0, 1, d.V);
   add(p->full_att_w, d.A, base + lay.w_full, d.A, 0, 1, d.A);
   add(p->full_att_b, 1, base + lay.b_full, 1, 0, 1, 1);
-  pack_jobs_kernel<<<dim3(64, jobs.n), 256, 0, st>>>(jobs);
+  pack_jobs_kernel<<<dim3(296, jobs.n), 256, 0, st>>>(jobs);
   DIC_LAUNCH_CHECK();
   return 0;
 }
