@@ -589,7 +589,7 @@ inline size_t attn_bwd_small_smem_bytes(int L, int A) {
 }
 
 template <typename ST>
-__global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const AttnBwdArgs p, int chunks) {
+__global__ void __launch_bounds__(kBwdSmallThreads, 2) attn_bwd_small_kernel(const AttnBwdArgs p, int chunks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = p.L, D = p.D, A = p.A;
   float* de_s = reinterpret_cast<float*>(smem_raw);
@@ -603,6 +603,20 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
   const float* hp = p.hp + (size_t)b * (A + D);
   ST* G = reinterpret_cast<ST*>(p.G) + (size_t)b * p.g_stride;
   Trace trace(p.trace);
+  // att1 is loop invariant: its first block of loads (the whole slab at the reference shape) is issued
+  // before the dependency wait and stays in flight through the softmax-backward reductions below
+  constexpr int IT = 13;     // 13 x 16 row groups >= 196 rows
+  const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)b * L * A;
+  Raw8<ST> raw0[IT];
+  if (A == 128) {
+    const int cg = tid & 15, rgp = tid >> 4;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int l = it * kBwdRowGroups + rgp;
+      if (l < L) raw0[it].load_stream(att1 + (size_t)l * A + cg * 8);
+      else raw0[it].zero();
+    }
+  }
   pdl_wait();
   pdl_trigger();
   trace.mark();
@@ -633,23 +647,13 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
   if (tid == 0) p.dbfull_part[b] = dbf;
 
   // relu-mask pass over att1.  red_s holds [2][kBwdRowGroups][A] partial sums.
-  const ST* att1 = reinterpret_cast<const ST*>(p.att1) + (size_t)b * L * A;
   if (A == 128) {
-    // reference shape: 16 column groups (8 columns, one 16-byte load) x 16 row groups; the image's
-    // whole att1 slab is put in flight before it is consumed (latency-bound kernel otherwise)
-    constexpr int IT = 13;     // 13 x 16 row groups >= 196 rows
+    // reference shape: 16 column groups (8 columns, one 16-byte load) x 16 row groups
     const int cg = tid & 15, rgp = tid >> 4;
     float a2[8], s1[8], s2[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) { a2[q] = att2_s[cg * 8 + q]; s1[q] = 0.f; s2[q] = 0.f; }
-    for (int l0 = 0; l0 < L; l0 += IT * kBwdRowGroups) {
-      Raw8<ST> raw[IT];
-#pragma unroll
-      for (int it = 0; it < IT; ++it) {
-        const int l = l0 + it * kBwdRowGroups + rgp;
-        if (l < L) raw[it].load_stream(att1 + (size_t)l * A + cg * 8);
-        else raw[it].zero();
-      }
+    auto consume = [&](const Raw8<ST> (&raw)[IT], int l0) {
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
         const int l = l0 + it * kBwdRowGroups + rgp;
@@ -664,6 +668,16 @@ __global__ void __launch_bounds__(kBwdSmallThreads) attn_bwd_small_kernel(const 
           }
         }
       }
+    };
+    consume(raw0, 0);                                        // the block prefetched before the dependency wait
+    for (int l0 = IT * kBwdRowGroups; l0 < L; l0 += IT * kBwdRowGroups) {     // L > 208 only
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int l = l0 + it * kBwdRowGroups + rgp;
+        if (l < L) raw0[it].load_stream(att1 + (size_t)l * A + cg * 8);
+        else raw0[it].zero();
+      }
+      consume(raw0, l0);
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
