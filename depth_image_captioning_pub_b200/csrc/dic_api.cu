@@ -127,6 +127,7 @@ static int hproj(const dic_dims& d, const Pack& pk, const ST* h, long long h_ld,
   g.sig_hi = d.A + d.D;
   g.fast_act = is_bf16;
   g.tag = 1;
+  g.b_static = 1;
   return gemm(g, st);
 }
 
@@ -157,6 +158,7 @@ static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long 
   g.split_mode = 1;
   g.split_stride = (long long)rows_alloc * 4 * d.H;
   g.tag = 2;
+  g.b_static = 1;
   *splits_out = s;
   return gemm(g, st);
 }
@@ -428,6 +430,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
                                   0, D, n, D, 4 * H, nullptr);
         g.b_n = 1; g.b_k = XW;
         g.tag = 3;
+        g.b_static = 1;
         DIC_TRY(gemm(g, sst));     // no split-K here: a memset node would break the PDL kernel chain
       }
 
@@ -458,6 +461,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
         g.split_mode = 1;
         g.split_stride = (long long)B * H;
         g.tag = 4;
+        g.b_static = 1;
         DIC_TRY(gemm(g, sst));
       }
     }
@@ -679,6 +683,7 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       const ST* hsrc = beam ? h_tmp + r0 * H : Xn + E + D;
       GemmArgs g = gemm_args_nt(hsrc, is_bf16, beam ? H : XW, pk.Wout(), is_bf16, H, lg, 0, V, Rs, V, H, pk.b_out());
       g.tag = 5;
+      g.b_static = 1;
       DIC_TRY(gemm(g, sst));
 
       if (!beam) {

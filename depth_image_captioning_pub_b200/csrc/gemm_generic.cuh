@@ -35,6 +35,8 @@ struct GemmArgs {
   int tag;                // call-site id for the timeline trace
   int bn;                 // tcgen05 engine: N tile width (32/64/128), 0 = chosen from the shape
   int fast_act;           // sigmoid through ex2.approx / rcp.approx (bf16 mode)
+  int b_static;           // B is a packed weight written at least two launches ago: the tcgen05 engine may
+                          // fetch its first tiles before the programmatic-dependency wait
 };
 
 inline GemmArgs gemm_args_nt(const void* A, int a_bf16, long long lda, const void* B, int b_bf16,

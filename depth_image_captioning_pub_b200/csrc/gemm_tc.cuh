@@ -141,6 +141,7 @@ struct TcArgs {
   int tiles_m, tiles_n;
   int tag;
   int fast_act;
+  int b_static;
   int dbg;               // DIC_GEMM_DEBUG=1: CTA 0 prints a globaltimer breakdown of its first tile
   TraceRec* trace;
 };
@@ -213,14 +214,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
-  if (dbg && threadIdx.x == 0) dbg_t[1] = gtimer();
-  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous
-  // kernel's tail; operands and the output buffer may only be touched after it has completed.
-  pdl_wait();
-  pdl_trigger();
-  trace.mark();
-  if (dbg && threadIdx.x == 0) dbg_t[2] = gtimer();
-
   // tile index -> (split, m block, n block); n fastest so that concurrent CTAs share the A tile in L2
   auto decode = [&](int t, int& split, int& m0, int& n0, int& kb0, int& kb1) {
     split = t / tiles_mn;
@@ -230,6 +223,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     kb0 = (int)(((long long)num_kb * split) / p.splits);
     kb1 = (int)(((long long)num_kb * (split + 1)) / p.splits);
   };
+  // Static B operand (a packed weight): the B halves of the first tile's first stages are requested
+  // BEFORE the dependency wait, so their latency overlaps the predecessor's tail; the A halves follow
+  // after the wait and complete the same mbarrier transaction counts.
+  int pre_b = 0;
+  if (p.b_static && threadIdx.x == 0 && (int)blockIdx.x < total) {
+    int split, m0, n0, kb0, kb1;
+    decode(blockIdx.x, split, m0, n0, kb0, kb1);
+    for (int kb = kb0; kb < kb1 && pre_b < kTcStages; ++kb, ++pre_b) {
+      const uint32_t sb = base + pre_b * STAGE_BYTES + A_BYTES;
+      mbar_expect_tx(full_bar(pre_b), STAGE_BYTES);
+      if (B_MN) {
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h)
+          tma_load_2d(sb + h * (kTcBK * 128), &tmB, full_bar(pre_b), n0 + 64 * h, kb * kTcBK);
+      } else {
+        tma_load_2d(sb, &tmB, full_bar(pre_b), kb * kTcBK, n0);
+      }
+    }
+  }
+  if (dbg && threadIdx.x == 0) dbg_t[1] = gtimer();
+  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous
+  // kernel's tail; operands and the output buffer may only be touched after it has completed.
+  pdl_wait();
+  pdl_trigger();
+  trace.mark();
+  if (dbg && threadIdx.x == 0) dbg_t[2] = gtimer();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -240,9 +259,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int split, m0, n0, kb0, kb1;
         decode(t, split, m0, n0, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
+          const bool b_done = pre_b > 0;       // this stage's B half (and expect_tx) went out before the wait
+          if (b_done) --pre_b;
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (!b_done) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          }
           if (A_MN) {
 #pragma unroll
             for (int h = 0; h < kTcBM / 64; ++h)
@@ -250,7 +273,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_2d(sa, &tmA, full_bar(stage), kb * kTcBK, m0);
           }
-          if (B_MN) {
+          if (b_done) {
+          } else if (B_MN) {
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h)
               tma_load_2d(sb + h * (kTcBK * 128), &tmB, full_bar(stage), n0 + 64 * h, kb * kTcBK);
@@ -581,6 +605,7 @@ inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   p.tiles_n = cdiv(g.N, BN);
   p.tag = g.tag;
   p.fast_act = g.fast_act;
+  p.b_static = g.b_static;
   p.trace = g_trace_host;
   {
     static int dbg_env = -1;
