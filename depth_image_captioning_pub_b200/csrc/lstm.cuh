@@ -27,13 +27,22 @@ struct LstmFwdArgs {
 template <typename ST>
 __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
   Trace trace(p.trace);
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const bool live = idx < p.rows * p.H;
+  const int H = p.H;
+  const int r = live ? idx / H : 0, j = live ? idx - r * H : 0;
+  // the previous cell state, the dropout mask and the bias are at least two launches old: loaded before the wait
+  float c_prev = 0.f, mk = 1.f, bias4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    c_prev = p.c_in[idx];
+    if (p.hdrop_out && p.mask) mk = p.mask[idx];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bias4[q] = p.bias_g[q * H + j];
+  }
   pdl_wait();
   pdl_trigger();
   trace.mark();
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= p.rows * p.H) { trace.end(TK_LSTM_FWD); return; }
-  const int r = idx / p.H, j = idx - r * p.H;
-  const int H = p.H;
+  if (!live) { trace.end(TK_LSTM_FWD); return; }
   // reduce the split-K partial tiles in a fixed order (deterministic); all loads are issued
   // before the adds so the up-to-64 L2 reads of a thread overlap
   float g4[4];
@@ -47,7 +56,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float s = p.bias_g[q * H + j];
+    float s = bias4[q];
 #pragma unroll
     for (int sp = 0; sp < kMaxSplits; ++sp) s += part[q][sp];
     g4[q] = s;
@@ -56,7 +65,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
   const float fg = sigmoidf_acc(g4[1]);
   const float gg = tanhf(g4[2]);
   const float og = sigmoidf_acc(g4[3]);
-  const float c = fg * p.c_in[idx] + ig * gg;
+  const float c = fg * c_prev + ig * gg;
   const float h = og * tanhf(c);
   p.c_out[idx] = c;
   if (p.acts) {
@@ -66,8 +75,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(const LstmFwdArgs p) {
   reinterpret_cast<ST*>(p.h_out)[(size_t)r * p.h_stride + j] = from_f<ST>(h);
   if (p.h_f32_out) p.h_f32_out[idx] = h;
   if (p.hdrop_out) {
-    const float m = p.mask ? p.mask[idx] : 1.f;
-    reinterpret_cast<ST*>(p.hdrop_out)[idx] = from_f<ST>(h * m);
+    reinterpret_cast<ST*>(p.hdrop_out)[idx] = from_f<ST>(h * mk);
   }
   trace.end(TK_LSTM_FWD);
 }
@@ -104,17 +112,27 @@ struct LstmBwdArgs {
 template <typename ST>
 __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
   Trace trace(p.trace);
+  // Forward state and the dc carry of step t+1 were written at least two launches ago: loaded before the
+  // dependency wait.  NOT dHout: for the last step it comes from the GEMM launched right before this kernel.
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const bool live = idx < p.rows * p.H;
+  const int H = p.H;
+  const int r = live ? idx / H : 0, j = live ? idx - r * H : 0;
+  float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, m = 1.f, dho = 0.f, cn = 0.f, cp = 0.f, dcc = 0.f;
+  if (live) {
+    const float* a = p.acts + (size_t)r * 4 * H;
+    ig = a[j]; fg = a[H + j]; gg = a[2 * H + j]; og = a[3 * H + j];
+    m = p.mask ? p.mask[idx] : 1.f;
+    cn = p.c_new[idx];
+    cp = p.c_prev[idx];
+    dcc = p.dc_carry[idx];
+  }
   pdl_wait();
   pdl_trigger();
   trace.mark();
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= p.rows * p.H) { trace.end(TK_LSTM_BWD); return; }
-  const int r = idx / p.H, j = idx - r * p.H;
-  const int H = p.H;
-  const float* a = p.acts + (size_t)r * 4 * H;
-  const float ig = a[j], fg = a[H + j], gg = a[2 * H + j], og = a[3 * H + j];
-  const float m = p.mask ? p.mask[idx] : 1.f;
-  float dh = p.dh_out[idx] * m;
+  if (!live) { trace.end(TK_LSTM_BWD); return; }
+  dho = p.dh_out[idx];
+  float dh = dho * m;
   if (r < p.dh_rows) {
     constexpr int kMaxSplits = 16;
     float part[kMaxSplits];
@@ -126,10 +144,10 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdArgs p) {
     for (int sp = 0; sp < kMaxSplits; ++sp) carry += part[sp];
     dh += carry;
   }
-  const float tc = tanhf(p.c_new[idx]);
-  const float dc = p.dc_carry[idx] + dh * og * (1.f - tc * tc);
+  const float tc = tanhf(cn);
+  const float dc = dcc + dh * og * (1.f - tc * tc);
   const float d_o = dh * tc;
-  const float d_i = dc * gg, d_g = dc * ig, d_f = dc * p.c_prev[idx];
+  const float d_i = dc * gg, d_g = dc * ig, d_f = dc * cp;
   p.dc_carry[idx] = dc * fg;
   ST* G = reinterpret_cast<ST*>(p.G) + (size_t)r * p.g_stride;
   G[j] = from_f<ST>(d_i * ig * (1.f - ig));
