@@ -470,7 +470,9 @@ struct AttnBwdArgs {
   const void* att1;      // [B, L, A] ST
   const float* hp;       // [B, A+D] fp32 att2 | beta   (this step)
   const float* z;        // [B, D] fp32                 (this step)
-  const float* dzg;      // [B, D] fp32
+  float* dzg;            // [B, D] fp32; dzg_rezero: cleared again after it is read (the next step's split-K GEMM
+                         // accumulates into it with red.add, two addends: order independent)
+  int dzg_rezero;
   const float* alpha;    // row b at alpha + b*alpha_stride
   long long alpha_stride;
   const float* dalpha;   // external gradient, same addressing, or null
@@ -510,6 +512,12 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
       else v0[r].zero();
     }
   }
+  // beta and z are forward state (static here): loaded before the wait as well
+  float beta[8], zz[8];
+  if (active) {
+    load8<float>(p.hp + (size_t)b * (A + D) + A + d, beta);
+    load8<float>(p.z + (size_t)b * D + d, zz);
+  }
   pdl_wait();       // dzg comes from the preceding GEMM; the annotation loads above are static
   pdl_trigger();
   trace.mark();
@@ -518,10 +526,9 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
 #pragma unroll
   for (int q = 0; q < 8; ++q) dz[q] = 0.f;
   if (active) {
-    float beta[8], g[8], zz[8];
-    load8<float>(p.hp + (size_t)b * (A + D) + A + d, beta);
+    float g[8];
     load8<float>(p.dzg + (size_t)b * D + d, g);
-    load8<float>(p.z + (size_t)b * D + d, zz);
+
     float db[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -531,6 +538,13 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
     if (rg == 0) {
       store8<ST>(reinterpret_cast<ST*>(p.DZ) + (size_t)b * D + d, dz);
       store8<ST>(reinterpret_cast<ST*>(p.G) + (size_t)b * p.g_stride + p.gcol_beta + d, db);
+    }
+  }
+  if (p.dzg_rezero) {
+    __syncthreads();          // every warp of the CTA has read its dzg values
+    if (active && rg == 0) {
+      const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store8<float>(p.dzg + (size_t)b * D + d, zero8);
     }
   }
 

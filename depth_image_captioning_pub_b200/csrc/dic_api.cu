@@ -390,6 +390,9 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   int dh_splits = cdiv((int)GW, kTcBK) / 4;      // >= 4 k-blocks of 64 per split
   if (dh_splits > kDhSplitsMax) dh_splits = kDhSplitsMax;
   if (dh_splits < 1) dh_splits = 1;
+  const bool dzg_split_ok = is_bf16 && tc_enabled() && cdiv(4 * H, kTcBK) >= 2 * kDzgSplits && D % 8 == 0 &&
+                            (long long)B * D >= 128LL * 128LL;
+  if (dzg_split_ok) DIC_CUDA(cudaMemsetAsync(dzg, 0, sizeof(float) * (size_t)B * D, st));
   int offs[DIC_MAX_STEPS + 1];
   offs[0] = 0;
   for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + sizes.n[t];
@@ -408,6 +411,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
       float* HPt = HP + ((size_t)t * B + r0) * (A + D);
       float* dhp = dh_part + (size_t)r0 * H;
       float* dzg_s = dzg + (size_t)r0 * D;
+      int dzg_splits = 1;
 
       LstmBwdArgs lb;
       memset(&lb, 0, sizeof(lb));
@@ -431,13 +435,19 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
         g.b_n = 1; g.b_k = XW;
         g.tag = 3;
         g.b_static = 1;
-        DIC_TRY(gemm(g, sst));     // no split-K here: a memset node would break the PDL kernel chain
+        // two K halves accumulated with red.add into a buffer that is zero on entry: 128 CTAs instead of 64.
+        // The buffer is cleared once before the loop and again by the streaming kernel right after it has read
+        // it (no memset node inside the PDL kernel chain); two addends onto zero: the result is order independent.
+        dzg_splits = dzg_split_ok ? kDzgSplits : 1;
+        g.splits = dzg_splits;
+        g.split_mode = 0;
+        DIC_TRY(gemm(g, sst));
       }
 
       AttnBwdArgs ab;
       memset(&ab, 0, sizeof(ab));
       ab.F = F + (size_t)r0 * L * D; ab.att1 = att1 + (size_t)r0 * L * A; ab.hp = HPt;
-      ab.z = Z + ((size_t)t * B + r0) * D; ab.dzg = dzg_s;
+      ab.z = Z + ((size_t)t * B + r0) * D; ab.dzg = dzg_s; ab.dzg_rezero = dzg_splits > 1;
       ab.alpha = alphas + ((size_t)r0 * T + t) * L; ab.alpha_stride = (long long)T * L;
       ab.dalpha = d_alphas ? d_alphas + ((size_t)r0 * T + t) * L : nullptr;
       ab.w_full = pk.w_full();

@@ -73,6 +73,7 @@ struct Pack {
 };
 
 constexpr int kGateSplitsMax = 16;
+constexpr int kDzgSplits = 2;        // K halves of the per-step dzg GEMM (atomic accumulation into a zeroed buffer)
 constexpr int kDhSplitsMax = 10;     // split-K partial buffers of the per-step dh GEMM (<= 16)
 
 // Training workspace (forward state saved for backward + backward scratch).
