@@ -253,6 +253,8 @@ def run_b200(args):
             loss = loss + LAM * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
         else:                       # fused loss head: same loss, same gradients
             loss = m.forward_loss(fr, fd, cp, lengths, ignore_index=V - 1, lam=LAM)
+        if allreduce is not None:
+            allreduce.arm()         # all-reduce starts as soon as the parameter gradients are enqueued
         loss.backward()
         if allreduce is not None:   # data parallel: one flat fp32 NCCL all-reduce over NVLink
             allreduce(average=True)

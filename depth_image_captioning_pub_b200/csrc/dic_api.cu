@@ -16,6 +16,10 @@
 
 namespace dic {
 thread_local char g_err[512] = {0};
+// event recorded by the next backward once every PARAMETER gradient is enqueued (before the dL/dF GEMM):
+// data-parallel callers start their all-reduce on it and overlap it with the dL/dF work
+// (process-wide, not thread-local: PyTorch runs backward on an autograd worker thread, not on the thread that armed it)
+static std::atomic<cudaEvent_t> g_grads_ready_event{nullptr};
 
 static int check_dims(const dic_dims* d, int dtype) {
   if (!d) DIC_FAIL(-1, "dims is null");
@@ -573,6 +577,10 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     DIC_TRY(launch_colsum(dl, dl_bf16, total, V, V, gr.lin_b, st));   // bf16 mode: half the bytes
   }
 
+  if (cudaEvent_t ev = g_grads_ready_event.exchange(nullptr)) {      // one shot
+    DIC_CUDA(cudaEventRecord(ev, st));
+  }
+
   // dL/dF = datt1 . W_enc + sum_t alpha_t (x) dz_t + dmeanF / L
   // (written in the annotations' dtype: fp32 in place, bf16 through the fp32 accumulation buffer dF32)
   if (d_feats && is_bf16 && dfeat_bf16 && dfeat_tc_eligible(A, D, lay.Lp)) {
@@ -789,6 +797,8 @@ int dic_trace_stop(unsigned int* count) {
   if (count) DIC_CUDA(cudaMemcpyFromSymbol(count, g_trace_cnt, sizeof(unsigned int)));
   return 0;
 }
+
+void dic_set_grads_ready_event(void* event) { g_grads_ready_event.store(reinterpret_cast<cudaEvent_t>(event)); }
 
 void dic_set_substreams(int n) { g_sub_override.store(n < 0 ? 0 : (n > kMaxSub ? kMaxSub : n)); }
 

@@ -42,6 +42,8 @@ class FlatGradAllReduce:
     def __init__(self, params: Sequence[torch.Tensor], module=None):
         self.params = [p for p in params]
         self.module = module
+        self._ready = None
+        self._comm = None
         if module is not None:
             module.flat_grads = True
         n = sum(p.numel() for p in self.params)
@@ -52,6 +54,20 @@ class FlatGradAllReduce:
         for p in self.params:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
+
+    def arm(self) -> None:
+        """Call right before loss.backward(): the library then records an event as soon as all parameter
+        gradients are enqueued (before the dL/dF GEMM), and __call__ runs the all-reduce on a side stream from
+        that point, overlapping the rest of backward."""
+        if self.module is None or not torch.cuda.is_available():
+            return
+        from . import _lib
+        if self._ready is None:
+            self._ready = torch.cuda.Event()
+            self._ready.record()                    # instantiates the underlying cudaEvent_t
+            self._comm = torch.cuda.Stream()
+        self._armed = True
+        _lib.load().dic_set_grads_ready_event(self._ready.cuda_event)
 
     def _in_place(self, average: bool, group) -> bool:
         m = self.module
@@ -65,12 +81,24 @@ class FlatGradAllReduce:
         grads = [p.grad for p in self.params]
         if any(g is None or g.data_ptr() not in ptrs for g in grads) or len(grads) != len(ptrs):
             return False
-        if average and dist.get_backend(group) == "nccl":
-            dist.all_reduce(e.grad_flat, op=dist.ReduceOp.AVG, group=group)
+        def reduce():
+            if average and dist.get_backend(group) == "nccl":
+                dist.all_reduce(e.grad_flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(e.grad_flat, op=dist.ReduceOp.SUM, group=group)
+                if average:
+                    e.grad_flat.mul_(1.0 / dist.get_world_size(group))
+        if getattr(self, "_armed", False) and e.grad_flat.is_cuda:
+            self._armed = False
+            main = torch.cuda.current_stream()
+            # (the library recorded _ready during backward, before its dL/dF GEMM: parameter gradients are
+            # complete from that point on)
+            self._comm.wait_event(self._ready)
+            with torch.cuda.stream(self._comm):
+                reduce()
+            main.wait_stream(self._comm)                # the optimizer step comes after the all-reduce
         else:
-            dist.all_reduce(e.grad_flat, op=dist.ReduceOp.SUM, group=group)
-            if average:
-                e.grad_flat.mul_(1.0 / dist.get_world_size(group))
+            reduce()
         return True
 
     def __call__(self, average: bool = True, group=None) -> None:

@@ -155,6 +155,11 @@ int dic_decoder_backward_ex(const dic_dims* dims, int dtype, int attn_mode, cons
                             const float* dropout_mask, const dic_params* grads, void* d_feats,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* One-shot hook for data-parallel training: the NEXT dic_decoder_backward(_ex) call of this process
+ * (any host thread: PyTorch runs backward on an autograd worker thread) records `event` (a cudaEvent_t) on its stream once all 17 parameter gradients are enqueued, i.e.
+ * before the dL/dF GEMM, so the caller's gradient all-reduce can overlap that last kernel.  NULL clears it. */
+void dic_set_grads_ready_event(void* event);
+
 /* ---- fused caption-loss head ----------------------------------------------
  * Replaces the caller-side loss of the training loop (depth_train.py:210-216 / :530-532):
  *   loss = cross_entropy(packed logits, packed targets, ignore_index, mean over non-ignored)
