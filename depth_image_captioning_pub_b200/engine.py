@@ -112,7 +112,9 @@ class Engine:
         B, T = f_rgb.shape[0], len(batch_sizes)
         total = int(sum(batch_sizes))
         logits = torch.empty(total, d.V, dtype=logits_dtype, device=self.device)
-        alphas = torch.zeros(B, T, d.L, dtype=torch.float32, device=self.device)
+        # padded steps of ragged captions must read as zeros (depth_models.py:176,201); equal lengths write every row
+        alloc = torch.zeros if batch_sizes[-1] < B else torch.empty
+        alphas = alloc(B, T, d.L, dtype=torch.float32, device=self.device)
         bs = (C.c_int32 * T)(*batch_sizes)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dic_decoder_forward_ex(
