@@ -214,9 +214,11 @@ __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) 
   }
   s = block_sum(s, scratch);
   // the thread that holds the target column reports the row's nll
-  const bool owner = valid && (tgt / 8) % 256 == tid && tgt < V;
+  const bool in_range = tgt >= 0 && tgt < V;
+  const bool owner = valid && in_range && (tgt / 8) % 256 == tid;
   if (owner) p.nll[r] = m + logf(s) - x_tgt;
-  if (!valid && tid == 0) p.nll[r] = 0.f;
+  if (tid == 0 && !valid) p.nll[r] = 0.f;
+  if (tid == 0 && valid && !in_range) p.nll[r] = nanf("");     // a target outside the vocabulary is a caller bug: make it visible
   const float scale = valid ? 1.f / p.count[0] : 0.f;
   const float ps = scale / s;
 #pragma unroll
