@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kCeThreads) loss_ce_row_kernel(const LossArgs 
       }
     }
     m = block_max(m, scratch);               // its barriers also publish row_s
-    const float x_tgt = valid ? row_s[tgt] : 0.f;
+    const float x_tgt = valid ? ((tgt >= 0 && tgt < V) ? row_s[tgt] : nanf("")) : 0.f;    // out-of-vocabulary target: NaN loss
     __syncthreads();                         // everyone has read x_tgt before row_s is overwritten
     float s = 0.f;
     if ((V & 3) == 0) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kCeThreads) loss_ce_row_kernel(const LossArgs 
   for (int v = tid; v < V; v += kCeThreads) s += expf(lg[v] - m);
   s = block_sum(s, scratch);
   const float lse = m + logf(s);
-  if (tid == 0) p.nll[r] = valid ? (lse - lg[tgt]) : 0.f;
+  if (tid == 0) p.nll[r] = valid ? ((tgt >= 0 && tgt < V) ? (lse - lg[tgt]) : nanf("")) : 0.f;
   const float scale = valid ? 1.f / p.count[0] : 0.f;
   for (int v = tid; v < V; v += kCeThreads)
     out[v] = from_f<ST>((expf(lg[v] - lse) - ((v == tgt) ? 1.f : 0.f)) * scale);
