@@ -41,6 +41,11 @@ struct AttnFwdArgs {
   bf16* alpha16_out;    // optional bf16 copy (A operand of the fused dL/dF GEMM), row r at + r*alpha16_stride
   long long alpha16_stride;
   int alpha16_width;    // padded row width Lp >= L: columns [L, Lp) are written as zeros
+  // Per-image hand-off alpha kernel -> context kernel (optional): the alpha CTA of image i publishes `epoch`
+  // in ready[i] (release) once its weights are written, and the context CTAs of image i poll it (acquire)
+  // instead of waiting for the whole alpha grid to drain and flush.
+  unsigned int* ready;  // [images] or null
+  unsigned int epoch;
   float* z_out;         // [rows, D] fp32 or null (saved for backward)
   void* zg_out;         // ST, row r at zg_out + r*zg_stride
   long long zg_stride;
@@ -216,6 +221,13 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
       for (int l = lane; l < p.alpha16_width; l += 32) a16[l] = __float2bfloat16_rn(l < L ? e[l] : 0.f);
     }
   }
+  if (p.ready && p.rpi <= 1) {             // one CTA per image (rpi == 0: KB rows, rpi == 1: its single row)
+    __syncthreads();                       // all rows of the image are written
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ready + img), "r"(p.epoch) : "memory");
+    }
+  }
   trace.end(TK_ALPHA);
 }
 
@@ -274,8 +286,21 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
 #pragma unroll
     for (int r = 0; r < U; ++r) v0[r].load_stream(F + (size_t)(rg + r * kCtxGroups) * D);
   }
-  // the annotations are static; alpha and beta come from the preceding kernels of this step
-  pdl_wait();
+  // the annotations are static; alpha and beta come from the preceding kernels of this step.  With the
+  // per-image hand-off the CTA waits for ITS image's attention weights only (beta was written two launches ago:
+  // the alpha CTAs passed their own dependency wait before this grid could start).
+  if (p.ready) {
+    if (tid == 0) {
+      unsigned int v, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready + img) : "memory");
+        if (++spins > (1u << 26)) __trap();
+      } while (v < p.epoch);
+    }
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
   pdl_trigger();
   trace.mark();
 

@@ -185,6 +185,12 @@ static int lstm_step(const dic_dims& d, const Pack& pk, const ST* X, long long X
   return launch_lstm_fwd<ST>(l, st);
 }
 
+static bool handoff_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DIC_HANDOFF"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 // Number of sub-batch streams of a time loop.  Measured on B200 (scripts/sub_sweep.py, gpurun_out/sweep1.log):
 // 2 streams gain 1% on the training step and lose 10% on decode, more streams lose everywhere -- the
 // streaming kernels fill every SM's register file (8 CTAs x 64 regs x 128 threads), so another
@@ -254,6 +260,11 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
     DIC_LAUNCH_CHECK();
   }
 
+  // per-image alpha -> context hand-off (soft / Gumbel-softmax; the one-hot Gumbel-max context kernel keeps the
+  // grid-level wait): flags cleared once per call, epoch = step + 1
+  unsigned int* ready = reinterpret_cast<unsigned int*>(ws + lay.ready);
+  const bool handoff = handoff_enabled() && attn_mode != DIC_ATTN_GUMBEL_MAX && pdl_enabled();
+  if (handoff) DIC_CUDA(cudaMemsetAsync(ready, 0, sizeof(unsigned int) * B, st));
   // time loop: S sub-batches of images on S streams (see common.cuh, "sub-batch streams")
   int offs[DIC_MAX_STEPS + 1];
   offs[0] = 0;
@@ -284,6 +295,7 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
       a.alpha16_out = alpha16 ? alpha16 + ((size_t)r0 * T + t) * lay.Lp : nullptr;
       a.alpha16_stride = (long long)T * lay.Lp;
       a.alpha16_width = lay.Lp;
+      if (handoff) { a.ready = ready + r0; a.epoch = (unsigned int)(t + 1); }
       a.z_out = Z + ((size_t)t * B + r0) * d.D;
       a.zg_out = X + d.E;
       a.zg_stride = (long long)XW;
