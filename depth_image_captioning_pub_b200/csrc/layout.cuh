@@ -80,7 +80,7 @@ constexpr int kDhSplitsMax = 10;     // split-K partial buffers of the per-step 
 struct TrainLayout {
   size_t Fsum, meanF, att1, XH, HP, Z, acts, c_all, gate_part, Hdrop;
   size_t G, DZ, de, dzg, dh, dc, dHout, dwfull_part, dbfull_part, datt1, dXemb, dmeanF, tmpvec, dlogits16, dal_part, h0, dF32, dh_part;
-  size_t alpha16, meanF16, hc0, dhc16, ready;
+  size_t alpha16, meanF16, hc0, dhc16, ready, done;
   int Lp;
   size_t bytes;
   size_t XW, GW;
@@ -122,6 +122,7 @@ struct TrainLayout {
     Lp = (d.L + 7) & ~7;
     alpha16 = c.take(TB * Lp * 2);     // bf16 alpha [B,T,Lp]: A operand of the fused dL/dF GEMM
     ready = c.take(sizeof(unsigned int) * B);   // per-image alpha -> context hand-off flags (epoch = step + 1)
+    done = c.take(sizeof(unsigned int) * B);    // per-image streaming-backward -> small-backward arrival counters
     meanF16 = c.take((size_t)B * d.D * 2);
     hc0 = c.take(sizeof(float) * B * 2 * d.H);
     dhc16 = c.take((size_t)B * 2 * d.H * 2);
