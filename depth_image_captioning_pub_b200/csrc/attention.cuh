@@ -512,10 +512,6 @@ struct AttnBwdArgs {
   int part_rows;
   int L, D, A;
   float inv_temp;
-  // Per-image hand-off streaming kernel -> small kernel (optional): every streaming CTA of image b bumps
-  // done[b] (after a fence) when its partials are written; the small CTA of image b polls for `chunks` arrivals
-  // instead of waiting for the whole streaming grid, then clears the counter for the next step.
-  unsigned int* done;   // [images] or null
   TraceRec* trace;
 };
 
@@ -619,11 +615,6 @@ __global__ void __launch_bounds__(kCtxThreads) attn_bwd_stream_kernel(const Attn
     s = warp_sum(s);
     if (lane == 0) part[l] = s;
   }
-  if (p.done) {
-    __threadfence();                 // this thread's partials / dz / dbeta' stores are visible device-wide ...
-    __syncthreads();                 // ... for every thread of the CTA before the arrival is published
-    if (tid == 0) atomicAdd(p.done + b, 1u);
-  }
   trace.end(TK_BWD_STREAM);
 }
 
@@ -664,19 +655,7 @@ __global__ void __launch_bounds__(kBwdSmallThreads, 2) attn_bwd_small_kernel(con
       else raw0[it].zero();
     }
   }
-  if (p.done) {
-    if (tid == 0) {
-      unsigned int v, spins = 0;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done + b) : "memory");
-        if (++spins > (1u << 26)) __trap();
-      } while (v < (unsigned int)chunks);
-      p.done[b] = 0u;                // next step's streaming CTAs start after this grid has completed
-    }
-    __syncthreads();
-  } else {
-    pdl_wait();
-  }
+  pdl_wait();
   pdl_trigger();
   trace.mark();
 

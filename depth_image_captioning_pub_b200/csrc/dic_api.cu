@@ -407,13 +407,6 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   int dh_splits = cdiv((int)GW, kTcBK) / 4;      // >= 4 k-blocks of 64 per split
   if (dh_splits > kDhSplitsMax) dh_splits = kDhSplitsMax;
   if (dh_splits < 1) dh_splits = 1;
-  unsigned int* done_cnt = reinterpret_cast<unsigned int*>(ws + lay.done);
-  // off: measured slower -- the polling small-backward CTAs become resident early and take register-file
-  // space from the streaming kernel (35.3 -> 38.0 us), DIC_BWD_HANDOFF=1 enables it
-  static int bwd_env = -1;
-  if (bwd_env < 0) { const char* e = getenv("DIC_BWD_HANDOFF"); bwd_env = (e && e[0] == '1') ? 1 : 0; }
-  const bool bwd_handoff = bwd_env == 1 && pdl_enabled();
-  if (bwd_handoff) DIC_CUDA(cudaMemsetAsync(done_cnt, 0, sizeof(unsigned int) * B, st));
   const bool dzg_split_ok = is_bf16 && tc_enabled() && cdiv(4 * H, kTcBK) >= 2 * kDzgSplits && D % 8 == 0 &&
                             (long long)B * D >= 128LL * 128LL;
   if (dzg_split_ok) DIC_CUDA(cudaMemsetAsync(dzg, 0, sizeof(float) * (size_t)B * D, st));
@@ -483,7 +476,6 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
       ab.dal_part = reinterpret_cast<float*>(ws + lay.dal_part) + (size_t)r0 * L;
       ab.part_rows = B;
       ab.L = L; ab.D = D; ab.A = A; ab.inv_temp = inv_temp;
-      if (bwd_handoff) ab.done = done_cnt + r0;
       DIC_TRY(launch_attn_bwd<ST>(ab, n, sst));
 
       // dh_{t-1} = [dgates | datt2 | dbeta'] . [W_hh ; W_dec ; W_beta]
