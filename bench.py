@@ -144,10 +144,38 @@ def synthetic_batch(B, seed, dtype=torch.float32):
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # ----------------------------------------------------------------------------------------------
 def cpu_train_step_factory(B):
+    """One training step of the reference CPU path on B captions -> (step fn, kind).
+
+    kind "reference": the UNMODIFIED reference decoder module (baseline/_ref, or /root/reference where it
+    exists; recipe oracle/make_ref.py) driven by the loss/optimizer lines of its own training loop
+    (depth_train.py:132-137,207-221).  kind "port": the oracle restatement, when the reference files did not
+    travel."""
     from oracle import decoder_oracle as O
-    w = {k: v.requires_grad_(True) for k, v in O.make_weights(A, E, D, H, V, seed=1234).items()}
+    from oracle import make_ref
     F_rgb, F_dep, caps, lengths = synthetic_batch(B, 1235)
-    F_dep.requires_grad_(True)
+    F_dep.requires_grad_(True)           # the depth CNN is trained (depth_train.py:136): dL/dF_depth is part of the step
+    ref, origin = make_ref.load_reference()
+    if ref is not None:
+        from torch.nn.utils.rnn import pack_padded_sequence
+        dec = ref.CD_RNNDecoderWithSoftAttention(A, E, D, H, V)      # dropout 0.5 (depth_train.py:115-120)
+        dec.load_state_dict(O.make_weights(A, E, D, H, V, seed=1234))
+        dec.train()
+        opt = torch.optim.AdamW(dec.parameters(), lr=1e-3)            # depth_train.py:136-137
+        loss_func = torch.nn.CrossEntropyLoss(ignore_index=V - 1)     # depth_train.py:132
+
+        def step():
+            opt.zero_grad()
+            F_dep.grad = None
+            outputs, alphas = dec(F_rgb, F_dep, caps, lengths)        # depth_train.py:207
+            targets = pack_padded_sequence(caps[:, 1:], [n - 1 for n in lengths], batch_first=True)
+            loss = loss_func(outputs.data, targets.data)              # :210-214
+            loss += LAM * ((1. - alphas.sum(dim=1)) ** 2).mean()      # :216
+            loss.backward()                                           # :219
+            opt.step()                                                # :221
+            return loss.item()                                        # :224
+        return step, "reference"
+
+    w = {k: v.requires_grad_(True) for k, v in O.make_weights(A, E, D, H, V, seed=1234).items()}
     opt = torch.optim.AdamW(list(w.values()), lr=1e-3)
     targets = O.pack_targets(caps, lengths)
 
@@ -162,19 +190,25 @@ def cpu_train_step_factory(B):
         loss.backward()
         opt.step()
         return float(loss.detach())
-    return step
+    return step, "port"
 
 
 def time_cpu(B, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_train_step_factory(B)
+    step, kind = cpu_train_step_factory(B)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return B * T * steps / dt, dt / steps
+    return B * T * steps / dt, dt / steps, kind
+
+
+def cpu_sample_text(B, steps, kind):
+    what = ("unmodified reference CD_RNNDecoderWithSoftAttention + its training-loop loss/AdamW lines "
+            "(depth_train.py:207-221)") if kind == "reference" else "oracle port of the reference CPU path as written"
+    return f"{steps} fwd+loss+bwd+AdamW steps on {B} of the 256 captions of a batch (fp32, {what})"
 
 
 def run_reference(args):
@@ -182,15 +216,18 @@ def run_reference(args):
     if rank != 0:
         return
     B = args.cpu_batch
-    tps, spstep = time_cpu(B, args.steps, args.warmup)
+    tps, spstep, kind = time_cpu(B, args.steps, min(args.warmup, 1))
     cores = torch.get_num_threads()
-    sample = f"fwd+loss+bwd+AdamW on {B} of the 256 captions per step (fp32, oracle port of the reference CPU path, as written)"
+    sample = cpu_sample_text(B, args.steps, kind)
+    cfg = workload_config(args.gpus, args.batch)
+    cfg["workload"] += f"; reference arm: each step is a bounded sample of {B} captions of that batch on the host cores"
+    cfg["reference_arm_sample_batch"] = B
     line = {
         "impl": "reference", "metric": "train_tokens_per_s", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": spstep * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, args.batch),
-        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -405,10 +442,9 @@ def run_b200(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        tps, _ = time_cpu(args.cpu_batch, args.cpu_steps, 1)
-        cpu = {"value": tps, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{args.cpu_steps} fwd+loss+bwd+AdamW steps on {args.cpu_batch} of the 256 captions "
-                         f"(fp32, oracle port of the reference CPU path as written)"}
+        tps, _, kind = time_cpu(args.cpu_batch, args.cpu_steps, 1)
+        cpu = {"value": tps, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": cpu_sample_text(args.cpu_batch, args.cpu_steps, kind)}
 
     if rank == 0:
         line = {

@@ -114,9 +114,14 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         from . import build as _build
         try:
             _build.build()
-        except Exception as e:  # stale-but-present library is still usable; missing is fatal
+        except Exception as e:
+            # A library that does not match the sources is never loaded silently: tests and benchmarks
+            # would run an old binary.  DIC_ALLOW_STALE_LIB=1 is the explicit escape hatch (e.g. a box
+            # without nvcc that was handed a prebuilt library of a different source revision).
             if not os.path.exists(LIB_PATH):
                 raise DicError(f"libdic.so is missing and could not be built: {e}") from e
+            if _build.is_stale() and os.environ.get("DIC_ALLOW_STALE_LIB") != "1":
+                raise DicError(f"libdic.so is stale (sources changed) and the rebuild failed: {e}") from e
     if not os.path.exists(LIB_PATH):
         raise DicError(f"{LIB_PATH} not found; run `python -m depth_image_captioning_pub_b200.build`")
     lib = C.CDLL(LIB_PATH)

@@ -56,14 +56,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB + ".tmp", os.path.join(CSRC, "dic_api.cu")]
+    tmp = f"{LIB}.{os.getpid()}.tmp"       # per process: spawned multi-GPU workers may all find the library stale
+    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(CSRC, "dic_api.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    os.replace(LIB + ".tmp", LIB)
+    os.replace(tmp, LIB)
     with open(LIB + ".hash", "w") as f:
         f.write(source_hash())
     if verbose:

@@ -407,11 +407,11 @@ inline bool bulk_ctx_enabled() { return bulk_ctx_mode() != 0; }
 
 template <typename ST, int KB>
 inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(attn_alpha_kernel<ST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     DIC_CUDA(cudaFuncSetAttribute(attn_context_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   {
     ProfScope prof(P_ATTN_ALPHA, st, (double)images * p.L * p.A * sizeof(ST));
@@ -421,10 +421,10 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
     if (per_image < 0) { const char* e = getenv("DIC_ALPHA_PER_IMAGE"); per_image = (e && e[0] == '0') ? 0 : 1; }
     if (KB > 1 && per_image) {
       // one CTA per IMAGE computing its KB rows from one read of the att1 slab
-      static bool attr2 = false;
-      if (!attr2) {
+      static DeviceOnce attr2;
+      if (int dev_ = 0; attr2.need(&dev_)) {
         DIC_CUDA(cudaFuncSetAttribute(attn_alpha_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr2 = true;
+        attr2.mark(dev_);
       }
       pa.rpi = 0;
       DIC_CUDA(launch_pdl(attn_alpha_kernel<ST, KB>, dim3(images), dim3(kAlphaThreads),
@@ -772,10 +772,10 @@ inline int launch_attn_bwd(const AttnBwdArgs& p_in, int rows, cudaStream_t st) {
     DIC_LAUNCH_CHECK();
   }
   {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (int dev_ = 0; attr_set.need(&dev_)) {
       DIC_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
+      attr_set.mark(dev_);
     }
     ProfScope prof(P_ATTN_BWD_SMALL, st, (double)rows * p.L * p.A * sizeof(ST));
     DIC_CUDA(launch_pdl(attn_bwd_small_kernel<ST>, dim3(rows), dim3(kBwdSmallThreads),

@@ -161,10 +161,10 @@ __global__ void __launch_bounds__(kBulkThreads) attn_context_bulk_kernel(const _
 
 template <typename ST, int KB>
 inline int launch_attn_context_bulk(const AttnFwdArgs& p, int images, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(attn_context_bulk_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   // the annotations as a row-major [images*L, D] matrix; box = 256 columns x 8 rows, no swizzle
   CUtensorMap tmF;

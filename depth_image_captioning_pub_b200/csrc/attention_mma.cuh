@@ -157,10 +157,10 @@ __global__ void __launch_bounds__(kMmaThreads) attn_context_mma_kernel(const __g
 
 template <int KB>
 inline int launch_attn_context_mma(const AttnFwdArgs& p, int images, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(attn_context_mma_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   CUtensorMap tmF;     // annotations as a row-major [images*L, D] bf16 matrix; box = 64 columns x 16 rows, 128B swizzle
   DIC_TRY(make_tmap_bf16(&tmF, p.F, (long long)images * p.L, p.D, p.D, kMmaRows));   // (L2 promotion: no effect measured)

@@ -93,6 +93,18 @@ struct ProfScope {
   }
 };
 
+// One-time-per-DEVICE guard (cudaFuncSetAttribute is a per-device setting, and two host threads -- the
+// caller's and PyTorch's autograd worker -- may reach a launch site at once: the flags are an atomic bit
+// mask; the guarded setup is idempotent, so two threads running it concurrently is harmless).
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool need(int* dev) {
+    cudaGetDevice(dev);
+    return ((done.load(std::memory_order_acquire) >> (*dev & 63)) & 1ull) == 0;
+  }
+  void mark(int dev) { done.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
 // ---- dtype-erased scalar access --------------------------------------------------------
 __device__ __forceinline__ float ld_as_float(const void* p, size_t i, int is_bf16) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p)[i])

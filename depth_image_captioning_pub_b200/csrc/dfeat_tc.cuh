@@ -495,11 +495,11 @@ inline int launch_dfeat_tc(const bf16* datt1, const bf16* Wenc, const bf16* alph
     q.trace = g_trace_host;
     const long long units = (long long)B * q.groups;
     const int grid2 = (int)(units < tc_num_sms() ? units : tc_num_sms());
-    static bool attr2 = false;
-    if (!attr2) {
+    static DeviceOnce attr2;
+    if (int dev_ = 0; attr2.need(&dev_)) {
       DIC_CUDA(cudaFuncSetAttribute(dfeat_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)dfeat2_smem_bytes()));
-      attr2 = true;
+      attr2.mark(dev_);
     }
     ProfScope prof(P_DFEAT, st, (double)B * L * D * 2);
     DIC_CUDA(launch_pdl(dfeat_gemm2_kernel, dim3(grid2), dim3(kTcThreads), dfeat2_smem_bytes(), st, tmA1, tmB1, tmA2,
@@ -514,11 +514,11 @@ inline int launch_dfeat_tc(const bf16* datt1, const bf16* Wenc, const bf16* alph
   p.trace = g_trace_host;
   const long long total = (long long)p.tiles_m * p.tiles_n;
   const int grid = (int)(total < tc_num_sms() ? total : tc_num_sms());
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(dfeat_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)dfeat_smem_bytes()));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   ProfScope prof(P_DFEAT, st, (double)B * L * D * 2);
   DIC_CUDA(launch_pdl(dfeat_gemm_kernel, dim3(grid), dim3(kTcThreads), dfeat_smem_bytes(), st, tmA1, tmB1, tmA2,

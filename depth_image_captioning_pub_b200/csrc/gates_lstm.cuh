@@ -249,11 +249,11 @@ inline int launch_gates_lstm(const bf16* X, long long x_ld, const bf16* Wgp, int
   GatesLstmArgs p;
   p.l = l; p.rows = rows; p.H = H; p.K = K; p.tiles_n = 4 * H / kGlBN; p.trace = g_trace_host;
   const int tiles = cdiv(rows, kTcBM) * p.tiles_n;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(gates_lstm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)gates_lstm_smem_bytes()));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   ProfScope prof(P_LSTM, st);
   cudaLaunchConfig_t cfg;

@@ -571,11 +571,11 @@ inline bool tc_gemm_eligible(const GemmArgs& g) {
 template <int BN, bool A_MN, bool B_MN>
 inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& p, int grid,
                           cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc_smem_bytes<BN>()));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   DIC_CUDA(launch_pdl(tc_gemm_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kTcThreads), tc_smem_bytes<BN>(), st, tmA, tmB,
                       p));

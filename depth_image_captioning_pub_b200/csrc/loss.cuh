@@ -308,10 +308,10 @@ inline int launch_caption_loss(LossArgs p, void* workspace, cudaStream_t st) {
   const int staged = row_bytes <= 200 * 1024 ? 1 : 0;
   if (!staged && (p.logits == p.d_logits || p.logits_bf16))
     DIC_FAIL(-4, "caption_loss: in-place / bf16 logits need V <= 51200");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(loss_ce_row_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   {
     ProfScope prof(P_LOSS, st, (double)p.N * p.V * ((p.logits_bf16 ? 2 : 4) + sizeof(ST)));

@@ -470,10 +470,10 @@ __global__ void __launch_bounds__(256) dfeat_accumulate_kernel(float* __restrict
 template <typename ST>
 inline int launch_dfeat_accumulate(float* dF, const float* alphas, const ST* DZ, const float* dmeanF, int B, int L,
                                    int D, int T, int accumulate, bf16* out16, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(dfeat_accumulate_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    attr_set.mark(dev_);
   }
   ProfScope prof(P_DFEAT, st, 2.0 * (double)B * L * D * sizeof(float));
   dim3 grid(cdiv(D, 512), B);

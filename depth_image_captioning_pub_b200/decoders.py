@@ -117,7 +117,7 @@ class _DecoderBase(nn.Module):
         eng = self._engine(features.shape[1], features.device)
         total = sum(bsz)
         mask = self._dropout_mask(total, features.device) if train_dropout else None
-        logits, alphas = DecoderFunction.apply(eng, attn_mode, captions, bsz, u, float(temp), mask, features,
+        logits, alphas = DecoderFunction.apply(eng, (attn_mode, torch.is_grad_enabled()), captions, bsz, u, float(temp), mask, features,
                                                depth_features, *self._param_list())
         packed = PackedSequence(logits, torch.tensor(bsz, dtype=torch.int64))
         return packed, alphas
@@ -137,7 +137,7 @@ class _DecoderBase(nn.Module):
         mask = self._dropout_mask(sum(bsz), features.device)
         if ignore_index is None:
             ignore_index = -100          # F.cross_entropy default
-        return CaptionLossFunction.apply(eng, attn_mode, captions, bsz, int(ignore_index), float(lam), u,
+        return CaptionLossFunction.apply(eng, (attn_mode, torch.is_grad_enabled()), captions, bsz, int(ignore_index), float(lam), u,
                                          float(temp), mask, features, depth_features, *self._param_list())
 
     def _draw_u(self, rows: int, L: int, device) -> torch.Tensor:

@@ -125,11 +125,11 @@ class Engine:
         return logits, alphas
 
     def backward(self, attn_mode: int, f_rgb, f_depth, captions, batch_sizes, d_logits, d_alphas, alphas,
-                 temp, dropout_mask, ws, param_shapes, need_dfeat: bool):
+                 temp, dropout_mask, ws, param_shapes, need_dfeat: bool, params=None):
         """d_logits: float32, or the storage dtype of the mode (what the fused loss head writes)."""
         d = self.dims
         B, T = f_rgb.shape[0], len(batch_sizes)
-        if self.use_flat_grads:
+        if self.use_flat_grads and not self._flat_buffer_is_live(params):
             grads = self._flat_grad_views(param_shapes)
         else:
             grads = [torch.empty(s, dtype=torch.float32, device=self.device) for s in param_shapes]
@@ -144,6 +144,17 @@ class Engine:
                 _lib.ptr(dropout_mask), C.byref(gs), _lib.ptr(d_feats), _lib.ptr(ws), ws.numel(),
                 _lib.stream_ptr(self.device)))
         return grads, d_feats
+
+    def _flat_buffer_is_live(self, params) -> bool:
+        """True when some p.grad still aliases the flat buffer (gradient accumulation, or
+        zero_grad(set_to_none=False)): writing this backward's gradients into the buffer would overwrite the
+        accumulated value and autograd's `p.grad += new` would then add the buffer to itself.  The backward
+        falls back to freshly allocated gradients and autograd accumulates them INTO the flat buffer."""
+        if self.grad_flat is None or params is None:
+            return False
+        lo = self.grad_flat.data_ptr()
+        hi = lo + self.grad_flat.numel() * 4
+        return any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params)
 
     def _flat_grad_views(self, param_shapes) -> List[torch.Tensor]:
         """Fresh view tensors into the persistent flat gradient buffer (autograd's AccumulateGrad takes
@@ -237,25 +248,34 @@ class Engine:
         return out
 
 
+def _needs_grad(grad_enabled: bool, params, f_rgb, f_depth) -> bool:
+    return bool(grad_enabled) and (any(p.requires_grad for p in params) or f_rgb.requires_grad
+                                   or (f_depth is not None and f_depth.requires_grad))
+
+
 class DecoderFunction(torch.autograd.Function):
     """Teacher-forced decoder forward/backward through dic_decoder_forward / _backward.
 
-    Inputs: engine, attn_mode, captions, batch_sizes, u, temp, dropout_mask, f_rgb, f_depth, *17 params.
+    Inputs: engine, grad_mode, captions, batch_sizes, u, temp, dropout_mask, f_rgb, f_depth, *17 params
+    (grad_mode = (attn_mode, torch.is_grad_enabled() of the CALLER: grad mode is always off inside
+    Function.forward, so it cannot be read here)).
     Outputs: packed logits [sum(bs), V], alphas [B, T, L].
     """
 
     @staticmethod
-    def forward(ctx, engine: Engine, attn_mode: int, captions, batch_sizes, u, temp, dropout_mask, f_rgb,
+    def forward(ctx, engine: Engine, grad_mode, captions, batch_sizes, u, temp, dropout_mask, f_rgb,
                 f_depth, *params):
-        needs_grad = torch.is_grad_enabled() and (
-            any(p.requires_grad for p in params) or f_rgb.requires_grad
-            or (f_depth is not None and f_depth.requires_grad))
+        attn_mode, grad_enabled = grad_mode
+        needs_grad = _needs_grad(grad_enabled, params, f_rgb, f_depth)
         engine.ensure_packed(params)
+        # a graph that will be differentiated owns its workspace (saved activations) until its backward;
+        # only no-grad forwards share the cached one
         ws = engine.train_workspace(f_rgb.shape[0], len(batch_sizes), fresh=needs_grad)
         logits, alphas = engine.forward(attn_mode, f_rgb, f_depth, captions, batch_sizes, u, temp,
                                         dropout_mask, ws)
         ctx.engine, ctx.attn_mode, ctx.batch_sizes, ctx.temp = engine, attn_mode, list(batch_sizes), temp
         ctx.ws = ws
+        ctx.params = params if needs_grad else None
         ctx.param_shapes = [tuple(p.shape) for p in params]
         ctx.pack_key = engine._pack_key
         ctx.has_depth = f_depth is not None
@@ -278,11 +298,15 @@ class DecoderFunction(torch.autograd.Function):
         d_logits = d_logits.contiguous().float()
         if d_alphas is not None:
             d_alphas = d_alphas.contiguous().float()
+        if ctx.ws is None:
+            raise DicError("this graph was already differentiated: its workspace is released after the first "
+                           "backward (retain_graph / double backward is not supported)")
         need_dfeat = ctx.needs_input_grad[7] or ctx.needs_input_grad[8]
         grads, d_feats = engine.backward(ctx.attn_mode, f_rgb, f_depth, captions, ctx.batch_sizes, d_logits,
                                          d_alphas, alphas, ctx.temp, dropout_mask, ctx.ws, ctx.param_shapes,
-                                         need_dfeat)
+                                         need_dfeat, params=ctx.params)
         ctx.ws = None
+        ctx.params = None
         d_rgb = d_feats if (ctx.needs_input_grad[7] and d_feats is not None) else None
         d_dep = None
         if ctx.has_depth and ctx.needs_input_grad[8] and d_feats is not None:
@@ -296,16 +320,15 @@ class CaptionLossFunction(torch.autograd.Function):
     loss = CE(packed logits, packed targets, ignore_index) + lam * mean((1 - sum_t alphas)^2)
     (depth_train.py:210-216).  The logits never reach the caller: the loss kernel turns them into
     d_logits (storage dtype) right away, and backward feeds those to dic_decoder_backward_ex.
-    Inputs: engine, attn_mode, captions, batch_sizes, ignore_index, lam, u, temp, dropout_mask,
-    f_rgb, f_depth, *17 params.  Output: loss (0-d fp32).
+    Inputs: engine, grad_mode, captions, batch_sizes, ignore_index, lam, u, temp, dropout_mask,
+    f_rgb, f_depth, *17 params (grad_mode as in DecoderFunction).  Output: loss (0-d fp32).
     """
 
     @staticmethod
-    def forward(ctx, engine: Engine, attn_mode: int, captions, batch_sizes, ignore_index, lam, u, temp,
+    def forward(ctx, engine: Engine, grad_mode, captions, batch_sizes, ignore_index, lam, u, temp,
                 dropout_mask, f_rgb, f_depth, *params):
-        needs_grad = torch.is_grad_enabled() and (
-            any(p.requires_grad for p in params) or f_rgb.requires_grad
-            or (f_depth is not None and f_depth.requires_grad))
+        attn_mode, grad_enabled = grad_mode
+        needs_grad = _needs_grad(grad_enabled, params, f_rgb, f_depth)
         engine.ensure_packed(params)
         ws = engine.train_workspace(f_rgb.shape[0], len(batch_sizes), fresh=needs_grad)
         # bf16 mode keeps the [sum(bs), V] logits block in bf16 (within the mode's 2e-2 bound on the logits):
@@ -317,6 +340,7 @@ class CaptionLossFunction(torch.autograd.Function):
                                                        alphas if lam != 0.0 else None, lam)
         ctx.engine, ctx.attn_mode, ctx.batch_sizes, ctx.temp = engine, attn_mode, list(batch_sizes), temp
         ctx.ws = ws
+        ctx.params = params if needs_grad else None
         ctx.param_shapes = [tuple(p.shape) for p in params]
         ctx.pack_key = engine._pack_key
         ctx.has_depth = f_depth is not None
@@ -336,13 +360,18 @@ class CaptionLossFunction(torch.autograd.Function):
         f_depth = f_depth if ctx.has_depth else None
         dropout_mask = dropout_mask if dropout_mask.numel() else None
         d_alphas = d_alphas if ctx.has_dalpha else None
+        if ctx.ws is None:
+            # the saved d_logits / d_alphas were scaled in place and the workspace released by the first backward
+            raise DicError("this graph was already differentiated (retain_graph / double backward is not "
+                           "supported by the fused loss node)")
         g = grad_loss.detach().reshape(1).to(device=f_rgb.device, dtype=torch.float32).contiguous()
         engine.scale_loss_grads(g, d_logits, d_alphas)        # device-side no-op when the upstream gradient is 1
         need_dfeat = ctx.needs_input_grad[9] or ctx.needs_input_grad[10]
         grads, d_feats = engine.backward(ctx.attn_mode, f_rgb, f_depth, captions, ctx.batch_sizes, d_logits,
                                          d_alphas, alphas, ctx.temp, dropout_mask, ctx.ws, ctx.param_shapes,
-                                         need_dfeat)
+                                         need_dfeat, params=ctx.params)
         ctx.ws = None
+        ctx.params = None
         d_rgb = d_feats if (ctx.needs_input_grad[9] and d_feats is not None) else None
         d_dep = d_feats if (ctx.has_depth and ctx.needs_input_grad[10] and d_feats is not None) else None
         return (None,) * 9 + (d_rgb, d_dep, *grads)
