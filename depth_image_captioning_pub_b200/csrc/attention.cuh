@@ -53,8 +53,57 @@ struct AttnFwdArgs {
   int mode;
   float inv_temp;
   int rpi;              // rows (beams) per image for the alpha kernel's row -> image map (0 = KB)
+  int skip_alpha;       // host side: the attention weights were already written by the fused head kernel (attn_head.cuh)
   TraceRec* trace;
 };
+
+// Normalisation of one row of energies by one warp (in place in shared memory), then the stores of the
+// attention weights: softmax | softmax((e+g)/temp) | one_hot(argmax(e+g))  (attention.py:90, :12-25, :34-48)
+__device__ __forceinline__ void attn_normalise_row(const AttnFwdArgs& p, float* e, int row, int lane) {
+  const int L = p.L;
+  const float* u = p.u ? p.u + (size_t)row * L : nullptr;
+  if (p.mode == DIC_ATTN_GUMBEL_MAX) {
+    // one_hot(argmax(e + g)), g = -log(-log u); ties -> lowest index (torch.argmax)
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int l = lane; l < L; l += 32) {
+      const float v = e[l] + (-logf(-logf(u[l])));
+      if (v > best) { best = v; bi = l; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;   // all NaN / -inf guard
+    for (int l = lane; l < L; l += 32) e[l] = (l == bi) ? 1.f : 0.f;
+  } else {
+    float m = -INFINITY;
+    for (int l = lane; l < L; l += 32) {
+      float v = e[l];
+      if (p.mode == DIC_ATTN_GUMBEL_SOFTMAX) v = (v + (-logf(-logf(u[l])))) * p.inv_temp;
+      e[l] = v;
+      m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      const float v = expf(e[l] - m);
+      e[l] = v;
+      s += v;
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int l = lane; l < L; l += 32) e[l] *= inv;
+  }
+  float* ao = p.alpha_out + (size_t)row * p.alpha_stride;
+  for (int l = lane; l < L; l += 32) ao[l] = e[l];
+  if (p.alpha16_out) {
+    bf16* a16 = p.alpha16_out + (size_t)row * p.alpha16_stride;
+    for (int l = lane; l < p.alpha16_width; l += 32) a16[l] = __float2bfloat16_rn(l < L ? e[l] : 0.f);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // (a) energies + normalisation.  Half-warp per annotation row (16 lanes x 8 columns = 128 columns
@@ -175,52 +224,7 @@ __global__ void __launch_bounds__(kAlphaThreads) attn_alpha_kernel(const AttnFwd
   __syncthreads();
 
   // normalisation: warp j owns row j (KB <= 8 warps)
-  if (warp < KB) {
-    const int j = warp;
-    float* e = e_s + j * Lp;
-    const float* u = p.u ? p.u + (size_t)(row0 + j) * L : nullptr;
-    if (p.mode == DIC_ATTN_GUMBEL_MAX) {
-      // one_hot(argmax(e + g)), g = -log(-log u); ties -> lowest index (torch.argmax)
-      float best = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int l = lane; l < L; l += 32) {
-        const float v = e[l] + (-logf(-logf(u[l])));
-        if (v > best) { best = v; bi = l; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      if (bi == 0x7fffffff) bi = 0;   // all NaN / -inf guard
-      for (int l = lane; l < L; l += 32) e[l] = (l == bi) ? 1.f : 0.f;
-    } else {
-      float m = -INFINITY;
-      for (int l = lane; l < L; l += 32) {
-        float v = e[l];
-        if (p.mode == DIC_ATTN_GUMBEL_SOFTMAX) v = (v + (-logf(-logf(u[l])))) * p.inv_temp;
-        e[l] = v;
-        m = fmaxf(m, v);
-      }
-      m = warp_max(m);
-      float s = 0.f;
-      for (int l = lane; l < L; l += 32) {
-        const float v = expf(e[l] - m);
-        e[l] = v;
-        s += v;
-      }
-      s = warp_sum(s);
-      const float inv = 1.f / s;
-      for (int l = lane; l < L; l += 32) e[l] *= inv;
-    }
-    float* ao = p.alpha_out + (size_t)(row0 + j) * p.alpha_stride;
-    for (int l = lane; l < L; l += 32) ao[l] = e[l];
-    if (p.alpha16_out) {
-      bf16* a16 = p.alpha16_out + (size_t)(row0 + j) * p.alpha16_stride;
-      for (int l = lane; l < p.alpha16_width; l += 32) a16[l] = __float2bfloat16_rn(l < L ? e[l] : 0.f);
-    }
-  }
+  if (warp < KB) attn_normalise_row(p, e_s + warp * Lp, row0 + warp, lane);
   if (p.ready && p.rpi <= 1) {             // one CTA per image (rpi == 0: KB rows, rpi == 1: its single row)
     __threadfence();                       // the writers' stores are visible device-wide ...
     __syncthreads();                       // ... before the flag goes up
@@ -413,7 +417,7 @@ inline int launch_attn_step_kb(const AttnFwdArgs& p, int images, cudaStream_t st
     DIC_CUDA(cudaFuncSetAttribute(attn_context_kernel<ST, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set.mark(dev_);
   }
-  {
+  if (!p.skip_alpha) {
     ProfScope prof(P_ATTN_ALPHA, st, (double)images * p.L * p.A * sizeof(ST));
     AttnFwdArgs pa = p;
     pa.trace = g_trace_host;

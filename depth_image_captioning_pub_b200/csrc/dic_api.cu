@@ -3,6 +3,7 @@
 #include "attention.cuh"
 #include "attention_bulk.cuh"
 #include "attention_mma.cuh"
+#include "attn_head.cuh"
 #include "common.cuh"
 #include "decode.cuh"
 #include "dfeat_tc.cuh"
@@ -284,7 +285,9 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
       ST* X = XH + ((size_t)t * B + r0) * XW;
       ST* Xn = XH + ((size_t)(t + 1) * B + r0) * XW;
       float* HPt = HP + ((size_t)t * B + r0) * (d.A + d.D);
-      DIC_TRY(hproj<ST>(d, pk, X + d.E + d.D, (long long)XW, n, HPt, sst));
+      // bf16 storage at the reference shape: h-projection + energies + softmax in one launch (attn_head.cuh)
+      const bool head = is_bf16 && !handoff && attn_head_eligible(d.A, d.H, d.D, d.L, 1);
+      if (!head) DIC_TRY(hproj<ST>(d, pk, X + d.E + d.D, (long long)XW, n, HPt, sst));
 
       AttnFwdArgs a;
       memset(&a, 0, sizeof(a));
@@ -303,6 +306,14 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
       a.L = d.L; a.D = d.D; a.A = d.A;
       a.mode = attn_mode;
       a.inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
+      if (head) {
+        HeadArgs hd;
+        hd.h = reinterpret_cast<const bf16*>(X + d.E + d.D); hd.h_ld = (long long)XW;
+        hd.Wdb = reinterpret_cast<const bf16*>(pk.Wdb(d)); hd.bias_db = pk.bias_db();
+        hd.HP = HPt; hd.a = a; hd.rows = n;
+        DIC_TRY(launch_attn_head(hd, sst));
+        a.skip_alpha = 1;
+      }
       DIC_TRY(launch_attn_step<ST>(a, n, 1, sst));
 
       float* gp = gate_part + (size_t)r0 * 4 * d.H;
@@ -683,7 +694,8 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       ST* X = XH + ((size_t)(t & 1) * R + r0) * XW;
       ST* Xn = XH + ((size_t)((t + 1) & 1) * R + r0) * XW;
       float* HPs = HP + r0 * (A + D);
-      DIC_TRY(hproj<ST>(d, pk, X + E + D, XW, Rs, HPs, sst));
+      const bool head = is_bf16 && attn_head_eligible(A, H, D, L, K);
+      if (!head) DIC_TRY(hproj<ST>(d, pk, X + E + D, XW, Rs, HPs, sst));
 
       AttnFwdArgs a;
       memset(&a, 0, sizeof(a));
@@ -696,6 +708,14 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       a.z_out = nullptr;
       a.zg_out = X + E; a.zg_stride = XW;
       a.L = L; a.D = D; a.A = A; a.mode = attn_mode; a.inv_temp = 1.f;
+      if (head) {
+        HeadArgs hd;
+        hd.h = reinterpret_cast<const bf16*>(X + E + D); hd.h_ld = XW;
+        hd.Wdb = reinterpret_cast<const bf16*>(pk.Wdb(d)); hd.bias_db = pk.bias_db();
+        hd.HP = HPs; hd.a = a; hd.rows = Rs;
+        DIC_TRY(launch_attn_head(hd, sst));
+        a.skip_alpha = 1;
+      }
       DIC_TRY(launch_attn_step<ST>(a, Bs, K, sst));
 
       float* gp = gate_part + r0 * 4 * H;

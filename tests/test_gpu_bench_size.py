@@ -124,7 +124,10 @@ def run_case(dev, precision, B, T, ragged, seed, fused, report):
     eloss = abs(float(loss.detach()) - loss_o) / max(1.0, abs(loss_o))
 
     if precision == "fp32":
-        ltol, atol, losstol, gtol, gtol_att, ftol_att = 1e-4, 1e-5, 1e-5, 1e-4, 1e-4, 1e-4
+        # The attention-projection gradients are sums over B*L rows whose mean-annotation part cancels exactly
+        # (sum_l de_l = 0 per caption-step): fp32 accumulation noise grows with the row count, and at this batch
+        # the CPU fp32 autograd of the reference itself is 2.5e-3 away from fp64 (scripts/grad_noise.py).
+        ltol, atol, losstol, gtol, gtol_att, ftol_att = 1e-4, 1e-5, 1e-5, 1e-4, 5e-3, 5e-3
     else:
         # bf16 storage: the spec bounds the logits (2e-2).  The attention-projection gradients pass through
         # softmax-backward and a ReLU mask whose pre-activations are perturbed ~1e-3 by ANY bf16 quantity
@@ -173,7 +176,8 @@ def test_bench_config_bf16_fused_step_vs_oracle(cuda_device):
         m.forward_loss(fr, fd, cp, lengths, ignore_index=V - 1, lam=0.7).backward()
     c = engine_counts(step)
     T = 20
-    assert c.get("gemm_tcgen05", 0) >= 5 * T + 10, c          # hproj, gates, dzg(x1), dh per step + out-of-loop GEMMs
+    assert c.get("gemm_tcgen05", 0) >= 3 * T + 10, c          # gates, dzg, dh per step + out-of-loop GEMMs
+    assert c.get("attn_alpha_fwd", 0) == T, c                 # fused head kernel (h-projection + energies + softmax)
     assert c.get("gemm_fma", 0) <= 4, c                       # (tiny out-of-loop products only)
     print("engine launches per step:", c)
     assert c.get("attn_context_fwd", 0) == T and c.get("attn_stream_bwd", 0) == T, c
@@ -189,7 +193,7 @@ def test_large_batch_vs_oracle(precision, ragged, cuda_device):
         c = engine_counts(lambda: m(fr, fd, cp, lengths))
         bsz = batch_sizes_from_lengths(lengths)
         big = sum(1 for n in bsz if n >= 128)
-        assert c.get("gemm_tcgen05", 0) >= 2 * big, (c, bsz)     # hproj + gates of every step with >= 128 rows
+        assert c.get("gemm_tcgen05", 0) >= big, (c, bsz)         # gate GEMM of every step with >= 128 rows
 
 
 def test_beam_128x5_vs_oracle(cuda_device):
