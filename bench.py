@@ -51,6 +51,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s: the BURST figure (these GEMMs are timed alone, ~50-100 us each)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
+    return 1650.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -256,8 +266,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        bind_to_gpu_numa_node(local)     # pinned host buffers next to this GPU's PCIe root (e2e H2D bandwidth)
+    bind_to_gpu_numa_node(local)         # pinned host buffers next to this GPU's PCIe root (e2e H2D bandwidth)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL banners / debug lines must not reach stdout
@@ -274,7 +283,6 @@ def run_b200(args):
     opt = P.FusedAdamW(params, lr=1e-3) if not args.torch_adamw else torch.optim.AdamW(params, lr=1e-3, fused=True)
     feat_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
     F_rgb_h, F_dep_h, caps_h, lengths = synthetic_batch(B, 1235 + rank, feat_dtype)
-    F_rgb_h, F_dep_h, caps_h = F_rgb_h.pin_memory(), F_dep_h.pin_memory(), caps_h.pin_memory()
     from depth_image_captioning_pub_b200.engine import batch_sizes_from_lengths
     targets = O.pack_targets(caps_h, lengths).to(dev)
     F_rgb = F_rgb_h.to(dev)
@@ -338,18 +346,37 @@ def run_b200(args):
     # its loss back.  The copies run on a side stream into one of two device buffer sets, one step
     # ahead of the compute (what a pin_memory DataLoader with non_blocking prefetch does), so a step
     # costs max(H2D, compute) instead of their sum; nothing is skipped or cached.
+    # The three inputs of a step (RGB annotations | depth annotations | captions) sit in ONE contiguous pinned slab
+    # (allocated after the rank was bound to its GPU's NUMA node: first touch on that socket), so a step is ONE
+    # cudaMemcpyAsync of 411 MB; the device side is a double-buffered slab with typed views into it.
+    nF = F_rgb_h.numel() * F_rgb_h.element_size()
+    nC = caps_h.numel() * 8
+    slab_h = torch.empty(2 * nF + nC, dtype=torch.uint8).pin_memory()
+    slab_h[:nF].view(feat_dtype).view_as(F_rgb_h).copy_(F_rgb_h)
+    slab_h[nF:2 * nF].view(feat_dtype).view_as(F_dep_h).copy_(F_dep_h)
+    slab_h[2 * nF:].view(torch.int64).view_as(caps_h).copy_(caps_h)
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(F_rgb), torch.empty_like(F_rgb), torch.empty_like(caps)) for _ in range(2)]
+    slabs = [torch.empty(2 * nF + nC, dtype=torch.uint8, device=dev) for _ in range(2)]
+    bufs = [(sl[:nF].view(feat_dtype).view_as(F_rgb), sl[nF:2 * nF].view(feat_dtype).view_as(F_rgb),
+             sl[2 * nF:].view(torch.int64).view_as(caps)) for sl in slabs]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"i": 0}
+    h2d = 2 * nF + nC
+
+    # pure host->device ceiling of this box for the same slab (no compute running), all ranks copying at once
+    def copy_only():
+        with torch.cuda.stream(copy_stream):
+            slabs[0].copy_(slab_h, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+    copy_only()
+    ms_copy = timed(copy_only, 10)
+    h2d_ceiling_gbs = h2d * 10 / (ms_copy * 1e-3) / 1e9          # per GPU, with all N ranks copying concurrently
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # previous user of this buffer set is done
-            bufs[slot][0].copy_(F_rgb_h, non_blocking=True)
-            bufs[slot][1].copy_(F_dep_h, non_blocking=True)
-            bufs[slot][2].copy_(caps_h, non_blocking=True)
+            slabs[slot].copy_(slab_h, non_blocking=True)
             ready[slot].record(copy_stream)
 
     for ev in consumed:
@@ -368,7 +395,7 @@ def run_b200(args):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
-    h2d = F_rgb_h.numel() * F_rgb_h.element_size() * 2 + caps_h.numel() * 8
+    e2e_gbs = h2d * args.steps / (ms_e2e * 1e-3) / 1e9
 
     # ---- per-kernel-class CUDA-event profile of the same steps (roofline) -------------------------
     lib.dic_profile_enable(1)
@@ -392,6 +419,54 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": dbytes / dcnt if dcnt else None,
                 "avg_launch_us": dms / dcnt * 1e3 if dcnt else None, "launches_per_step": dcnt // args.steps}
 
+    # ---- the three big out-of-loop GEMMs against their own roofs (same profiled steps, timed alone by events) ----
+    tpeak, tpeak_src = measured_tensor_peak()
+    N_rows = B * T
+    gemm_shapes = {
+        # class: (kernel, flops, algorithmic bytes)
+        "gemm_att1": ("att1 = F.W_enc^T (tc_gemm_kernel, once per step)", 2.0 * B * L * A * D, B * L * (D + A) * 2.0),
+        "gemm_logits": ("logits = dropout(h).W_out^T, bf16 out (tc_gemm_kernel)", 2.0 * N_rows * V * H,
+                        N_rows * V * 2.0 + N_rows * H * 2.0),
+        "dfeat_accumulate": ("dL/dF = [datt1|alpha^T].[W_enc;dz] (dfeat_gemm_kernel)", 2.0 * B * L * D * (A + T),
+                             B * L * D * 2.0 + B * L * A * 2.0 + B * T * (D + L) * 2.0),
+    }
+    roofline_gemm = []
+    for cls, (name, flops, nbytes) in gemm_shapes.items():
+        if cls in prof and prof[cls][1]:
+            us = prof[cls][0] / prof[cls][1] * 1e3
+            tf = flops / (us * 1e-6) / 1e12
+            gbs = nbytes / (us * 1e-6) / 1e9
+            roofline_gemm.append({"kernel": name, "avg_launch_us": us, "tflops": tf, "frac_tensor": tf / tpeak,
+                                  "gbs": gbs, "frac_hbm": gbs / peak, "bound": "hbm" if gbs / peak > tf / tpeak else "tensor"})
+
+    # ---- BASELINE.json configs[4] per-GPU work: 512 captions per GPU (global 4096 on 8 GPUs) -------------------
+    config5 = None
+    if not args.no_config5:
+        B5 = 512
+        Fr5, Fd5, caps5, lengths5 = synthetic_batch(B5, 2235 + rank, feat_dtype)
+        Fr5, caps5 = Fr5.to(dev), caps5.to(dev)
+        Fd5 = Fd5.to(dev).requires_grad_(True)
+
+        def step5():
+            loss = m.forward_loss(Fr5, Fd5, caps5, lengths5, ignore_index=V - 1, lam=LAM)
+            if allreduce is not None:
+                allreduce.arm()
+            loss.backward()
+            if allreduce is not None:
+                allreduce(average=True)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            Fd5.grad = None
+        for _ in range(3):
+            step5()
+        s5 = max(5, args.steps // 2)
+        ms5 = timed(step5, s5)
+        config5 = {"workload": "BASELINE.json configs[4]: depth-soft data-parallel training, 512 captions per GPU",
+                   "batch_per_gpu": B5, "global_batch": B5 * world, "steps": s5, "ms_per_step": ms5 / s5,
+                   "tokens_per_s": B5 * T * world * s5 / (ms5 * 1e-3)}
+        del Fr5, Fd5, caps5
+        torch.cuda.empty_cache()
+
     # ---- beam-5 decode (second half of the BASELINE metric), 128 images per GPU --------------------
     extra = {}
     if not args.no_beam:
@@ -405,6 +480,16 @@ def run_b200(args):
         ms_b = timed(lambda: m.beam_search(fr, fd, voc, beam=5, max_length=T), args.steps)
         extra["beam5_captions_per_s"] = Bd * world * args.steps / (ms_b * 1e-3)
         extra["beam5_config"] = {"images_per_gpu": Bd, "beam": 5, "max_len": T}
+        # HBM roofline of beam decode: per caption T*(L*D + L*A)*2 bytes streamed (the annotations are
+        # read once per image-step for all 5 beams) + 3*L*D*2 for the prologue (RGB + depth in, sum out)
+        cap_bytes = T * (L * D + L * A) * 2.0 + 3.0 * L * D * 2.0
+        per_gpu = Bd * args.steps / (ms_b * 1e-3)
+        extra["beam5_roofline"] = {"bound": "hbm", "algorithmic_bytes_per_caption": cap_bytes,
+                                   "ceiling_captions_per_s_per_gpu": peak * 1e9 / cap_bytes,
+                                   "achieved_captions_per_s_per_gpu": per_gpu,
+                                   "achieved_gbs": per_gpu * cap_bytes / 1e9, "peak_gbs": peak,
+                                   "frac": per_gpu * cap_bytes / 1e9 / peak,
+                                   "us_per_decode_step": ms_b / args.steps / T * 1e3}
         for _ in range(2):      # first call loads the single-beam kernels and allocates its workspace
             m.batch_sample(fr, fd, voc, max_length=T)
         ms_g = timed(lambda: m.batch_sample(fr, fd, voc, max_length=T), args.steps)
@@ -453,10 +538,12 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic", "config": workload_config(world, B),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps,
-                    "note": "host->device copy of each step's inputs on a side stream, one step ahead (double buffered)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kernels, "extra": extra,
+                    "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_gpu": e2e_gbs,
+                    "h2d_ceiling_gbs_per_gpu": h2d_ceiling_gbs, "frac_of_h2d_ceiling": e2e_gbs / h2d_ceiling_gbs,
+                    "note": "one cudaMemcpyAsync of the step's input slab (pinned, NUMA-local) on a side stream, one step "
+                            "ahead (double buffered); ceiling = the same copy with no compute, all ranks at once"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_gemm": roofline_gemm,
+            "cpu_baseline": cpu, "kernels": kernels, "config5": config5, "extra": extra,
         }
         emit(line)
     if world > 1:
@@ -479,6 +566,7 @@ def main():
     ap.add_argument("--torch-adamw", action="store_true", help="step torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-beam", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 512-captions-per-GPU run (BASELINE configs[4])")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -52,13 +52,13 @@ inline std::atomic<long long> g_launches{0};
 
 enum ProfClass {
   P_ATTN_FWD = 0, P_ATTN_BWD, P_DATT1, P_GEMM_TC, P_GEMM_FMA, P_LSTM, P_FUSE, P_COLSUM,
-  P_ATTN_ALPHA, P_ATTN_BWD_SMALL, P_DFEAT, P_BEAM_SELECT, P_DECODE_MISC, P_LOSS, P_N
+  P_ATTN_ALPHA, P_ATTN_BWD_SMALL, P_DFEAT, P_BEAM_SELECT, P_DECODE_MISC, P_LOSS, P_GEMM_ATT1, P_GEMM_LOGITS, P_N
 };
 inline const char* prof_class_name(int c) {
   static const char* names[P_N] = {"attn_context_fwd", "attn_stream_bwd", "datt1", "gemm_tcgen05",
                                    "gemm_fma", "lstm_pointwise", "fuse_feats", "colsum",
                                    "attn_alpha_fwd", "attn_small_bwd", "dfeat_accumulate",
-                                   "beam_select", "decode_misc", "caption_loss"};
+                                   "beam_select", "decode_misc", "caption_loss", "gemm_att1", "gemm_logits"};
   return (c >= 0 && c < P_N) ? names[c] : "?";
 }
 struct ProfState {

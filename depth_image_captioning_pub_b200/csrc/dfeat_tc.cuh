@@ -479,7 +479,9 @@ inline bool dfeat_tc_eligible(int A, int D, int Lp) {
 // dz [T, B, D] bf16 (inactive rows zero); dmeanF [B, D] fp32; dF [B*L, D] bf16
 inline int launch_dfeat_tc(const bf16* datt1, const bf16* Wenc, const bf16* alpha16, int Lp, const bf16* dz,
                            const float* dmeanF, bf16* dF, int B, int L, int D, int A, int T,
-                           cudaStream_t st) {
+                           cudaStream_t st, int reserve_sms = 0) {
+  // reserve_sms: SMs left free for a gradient all-reduce running next to this (persistent, one CTA per SM) kernel
+  const int max_ctas = tc_num_sms() - reserve_sms > 8 ? tc_num_sms() - reserve_sms : 8;
   CUtensorMap tmA1, tmB1, tmA2, tmB2;
   DIC_TRY(make_tmap_bf16(&tmA1, datt1, (long long)B * L, A, A, kTcBM));          // K-major: [rows, A], box 128 x 64
   DIC_TRY(make_tmap_bf16(&tmB1, Wenc, A, D, D, kTcBK));                          // MN-major: [A rows, D], box 64 x 64
@@ -494,7 +496,7 @@ inline int launch_dfeat_tc(const bf16* datt1, const bf16* Wenc, const bf16* alph
     q.groups = cdiv(cdiv(D, 128), kDf2NG);
     q.trace = g_trace_host;
     const long long units = (long long)B * q.groups;
-    const int grid2 = (int)(units < tc_num_sms() ? units : tc_num_sms());
+    const int grid2 = (int)(units < max_ctas ? units : max_ctas);
     static DeviceOnce attr2;
     if (int dev_ = 0; attr2.need(&dev_)) {
       DIC_CUDA(cudaFuncSetAttribute(dfeat_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -513,7 +515,7 @@ inline int launch_dfeat_tc(const bf16* datt1, const bf16* Wenc, const bf16* alph
   p.tiles_n = cdiv(D, 128);
   p.trace = g_trace_host;
   const long long total = (long long)p.tiles_m * p.tiles_n;
-  const int grid = (int)(total < tc_num_sms() ? total : tc_num_sms());
+  const int grid = (int)(total < max_ctas ? total : max_ctas);
   static DeviceOnce attr_set;
   if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(dfeat_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

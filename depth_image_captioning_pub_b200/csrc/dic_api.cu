@@ -21,6 +21,12 @@ thread_local char g_err[512] = {0};
 // data-parallel callers start their all-reduce on it and overlap it with the dL/dF work
 // (process-wide, not thread-local: PyTorch runs backward on an autograd worker thread, not on the thread that armed it)
 static std::atomic<cudaEvent_t> g_grads_ready_event{nullptr};
+// optional earlier hand-over points of the same backward (buckets of the flat gradient buffer, in its order):
+// the vocabulary-projection gradients (last two tensors) are final before the time loop starts, everything
+// but the encoder_att pair (first two tensors) is final before the datt1 / dW_enc contraction
+static std::atomic<cudaEvent_t> g_grads_lin_event{nullptr};
+static std::atomic<cudaEvent_t> g_grads_mid_event{nullptr};
+constexpr int kAllReduceSms = 20;   // SMs the persistent dL/dF GEMM leaves to an overlapped all-reduce
 
 static int check_dims(const dic_dims* d, int dtype) {
   if (!d) DIC_FAIL(-1, "dims is null");
@@ -95,6 +101,8 @@ static int prologue(const dic_dims& d, const Pack& pk, const void* f_rgb, const 
   // att1 = F . W_enc^T + b_enc   (attention.py:84, hoisted out of the time loop)
   GemmArgs g = gemm_args_nt(F, is_bf16, d.D, pk.Wenc(), is_bf16, d.D, att1, is_bf16, d.A, B * d.L, d.A,
                             d.D, pk.b_enc());
+  g.prof = P_GEMM_ATT1;
+  g.prof_bytes = (double)B * d.L * ((double)d.D + d.A) * sizeof(ST);
   DIC_TRY(gemm(g, st));
   return 0;
 }
@@ -337,6 +345,8 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
   // PackedSequence (time-major) order
   GemmArgs g = gemm_args_nt(Hdrop, is_bf16, d.H, pk.Wout(), is_bf16, d.H, logits, logits_bf16, d.V, total, d.V,
                             d.H, pk.b_out());
+  g.prof = P_GEMM_LOGITS;
+  g.prof_bytes = (double)total * d.V * (logits_bf16 ? 2 : 4);
   DIC_TRY(gemm(g, st));
   return 0;
 }
@@ -411,6 +421,16 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     GemmArgs g = gemm_args_nt(dl, dl_bf16, V, pk.Wout(), is_bf16, 0, dHout, 0, H, total, H, V, nullptr);
     g.b_n = 1; g.b_k = H;
     DIC_TRY(gemm_splitk(g, st));
+  }
+
+  // linear (vocabulary projection): its gradients need d_logits and the saved dropout(h) only, so they are
+  // final before the time loop starts -- a data-parallel caller reduces them under the whole loop
+  {
+    GemmArgs g = gemm_args_nt(dl, dl_bf16, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
+    g.a_m = 1; g.a_k = V; g.b_n = 1; g.b_k = H;
+    DIC_TRY(gemm_splitk(g, st));
+    DIC_TRY(launch_colsum(dl, dl_bf16, total, V, V, gr.lin_b, st));   // bf16 mode: half the bytes
+    if (cudaEvent_t ev = g_grads_lin_event.exchange(nullptr)) DIC_CUDA(cudaEventRecord(ev, st));
   }
 
   const float inv_temp = attn_mode == DIC_ATTN_GUMBEL_SOFTMAX ? 1.f / temp : 1.f;
@@ -583,6 +603,8 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   DIC_TRY(launch_colsum(dwfull_part, 0, (int)TB, A, A, gr.full_att_w, st));
   DIC_TRY(launch_colsum(dbfull_part, 0, (int)TB, 1, 1, gr.full_att_b, st));
 
+  if (cudaEvent_t ev = g_grads_mid_event.exchange(nullptr)) DIC_CUDA(cudaEventRecord(ev, st));
+
   // encoder_att: datt1 summed over steps, then two contractions over B*L rows
   {
     Datt1Args da;
@@ -593,17 +615,8 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     DIC_TRY(wgrad(datt1, A, A, F, D, D, B * L, gr.enc_att_w, D));
   }
 
-  // linear (vocabulary projection)
-  {
-    GemmArgs g = gemm_args_nt(dl, dl_bf16, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
-    g.a_m = 1; g.a_k = V; g.b_n = 1; g.b_k = H;
-    DIC_TRY(gemm_splitk(g, st));
-    DIC_TRY(launch_colsum(dl, dl_bf16, total, V, V, gr.lin_b, st));   // bf16 mode: half the bytes
-  }
-
-  if (cudaEvent_t ev = g_grads_ready_event.exchange(nullptr)) {      // one shot
-    DIC_CUDA(cudaEventRecord(ev, st));
-  }
+  const cudaEvent_t ev_all = g_grads_ready_event.exchange(nullptr);     // one shot
+  if (ev_all) DIC_CUDA(cudaEventRecord(ev_all, st));
 
   // dL/dF = datt1 . W_enc + sum_t alpha_t (x) dz_t + dmeanF / L
   // (written in the annotations' dtype: fp32 in place, bf16 through the fp32 accumulation buffer dF32)
@@ -612,7 +625,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     DIC_TRY(launch_dfeat_tc(reinterpret_cast<const bf16*>(datt1), reinterpret_cast<const bf16*>(pk.Wenc()),
                             reinterpret_cast<const bf16*>(ws + lay.alpha16), lay.Lp,
                             reinterpret_cast<const bf16*>(DZ), dmeanF, reinterpret_cast<bf16*>(d_feats), B, L, D, A,
-                            T, st));
+                            T, st, ev_all ? kAllReduceSms : 0));
   } else if (d_feats) {
     float* acc = dfeat_bf16 ? reinterpret_cast<float*>(ws + lay.dF32) : reinterpret_cast<float*>(d_feats);
     GemmArgs g = gemm_args_nt(datt1, is_bf16, A, pk.Wenc(), is_bf16, 0, acc, 0, D, B * L, D, A, nullptr);
@@ -832,6 +845,11 @@ int dic_trace_stop(unsigned int* count) {
 }
 
 void dic_set_grads_ready_event(void* event) { g_grads_ready_event.store(reinterpret_cast<cudaEvent_t>(event)); }
+void dic_set_grads_ready_events(void* ev_linear, void* ev_middle, void* ev_all) {
+  g_grads_lin_event.store(reinterpret_cast<cudaEvent_t>(ev_linear));
+  g_grads_mid_event.store(reinterpret_cast<cudaEvent_t>(ev_middle));
+  g_grads_ready_event.store(reinterpret_cast<cudaEvent_t>(ev_all));
+}
 
 void dic_set_substreams(int n) { g_sub_override.store(n < 0 ? 0 : (n > kMaxSub ? kMaxSub : n)); }
 

@@ -37,6 +37,8 @@ struct GemmArgs {
   int fast_act;           // sigmoid through ex2.approx / rcp.approx (bf16 mode)
   int b_static;           // B is a packed weight written at least two launches ago: the tcgen05 engine may
                           // fetch its first tiles before the programmatic-dependency wait
+  int prof;               // event-profile class of this launch (0 = the engine's default class)
+  double prof_bytes;      // algorithmic bytes attributed to it
 };
 
 inline GemmArgs gemm_args_nt(const void* A, int a_bf16, long long lda, const void* B, int b_bf16,

@@ -614,7 +614,7 @@ inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
   const int grid = (int)(total < tc_num_sms() ? total : tc_num_sms());
-  ProfScope prof(P_GEMM_TC, st);
+  ProfScope prof(g.prof ? g.prof : (int)P_GEMM_TC, st, g.prof_bytes);
   if constexpr (BN >= 64) {
     if (!a_mn && b_mn) return tc_gemm_launch<BN, false, true>(tmA, tmB, p, grid, st);
     if (a_mn && b_mn) return tc_gemm_launch<BN, true, true>(tmA, tmB, p, grid, st);

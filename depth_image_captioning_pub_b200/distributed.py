@@ -56,18 +56,27 @@ class FlatGradAllReduce:
             o += p.numel()
 
     def arm(self) -> None:
-        """Call right before loss.backward(): the library then records an event as soon as all parameter
-        gradients are enqueued (before the dL/dF GEMM), and __call__ runs the all-reduce on a side stream from
-        that point, overlapping the rest of backward."""
+        """Call right before loss.backward(): the library then records three events while it enqueues the
+        backward -- vocabulary-projection gradients final (before the time loop), everything but the
+        encoder_att pair final, all final (before the dL/dF GEMM) -- and __call__ reduces the three matching
+        slices of the flat buffer on a side stream from those points, overlapping the rest of backward."""
         if self.module is None or not torch.cuda.is_available():
             return
         from . import _lib
         if self._ready is None:
-            self._ready = torch.cuda.Event()
-            self._ready.record()                    # instantiates the underlying cudaEvent_t
+            self._ready = [torch.cuda.Event() for _ in range(3)]
+            for ev in self._ready:
+                ev.record()                         # instantiates the underlying cudaEvent_t
             self._comm = torch.cuda.Stream()
         self._armed = True
-        _lib.load().dic_set_grads_ready_event(self._ready.cuda_event)
+        _lib.load().dic_set_grads_ready_events(*[ev.cuda_event for ev in self._ready])
+
+    def _buckets(self, flat: torch.Tensor):
+        """(linear, middle, encoder_att) slices of the flat buffer, in the order their events fire."""
+        sizes = [p.numel() for p in self.params]
+        n = flat.numel()
+        head, tail = sizes[0] + sizes[1], sizes[-2] + sizes[-1]
+        return [flat[n - tail:], flat[head:n - tail], flat[:head]]
 
     def _in_place(self, average: bool, group) -> bool:
         m = self.module
@@ -81,24 +90,24 @@ class FlatGradAllReduce:
         grads = [p.grad for p in self.params]
         if any(g is None or g.data_ptr() not in ptrs for g in grads) or len(grads) != len(ptrs):
             return False
-        def reduce():
+
+        def reduce(t):
             if average and dist.get_backend(group) == "nccl":
-                dist.all_reduce(e.grad_flat, op=dist.ReduceOp.AVG, group=group)
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
             else:
-                dist.all_reduce(e.grad_flat, op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
                 if average:
-                    e.grad_flat.mul_(1.0 / dist.get_world_size(group))
-        if getattr(self, "_armed", False) and e.grad_flat.is_cuda:
+                    t.mul_(1.0 / dist.get_world_size(group))
+        if getattr(self, "_armed", False) and e.grad_flat.is_cuda and len(self.params) >= 5:
             self._armed = False
             main = torch.cuda.current_stream()
-            # (the library recorded _ready during backward, before its dL/dF GEMM: parameter gradients are
-            # complete from that point on)
-            self._comm.wait_event(self._ready)
             with torch.cuda.stream(self._comm):
-                reduce()
+                for ev, part in zip(self._ready, self._buckets(e.grad_flat)):
+                    self._comm.wait_event(ev)       # recorded by the library inside this step's backward
+                    reduce(part)
             main.wait_stream(self._comm)                # the optimizer step comes after the all-reduce
         else:
-            reduce()
+            reduce(e.grad_flat)
         return True
 
     def __call__(self, average: bool = True, group=None) -> None:

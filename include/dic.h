@@ -159,6 +159,12 @@ int dic_decoder_backward_ex(const dic_dims* dims, int dtype, int attn_mode, cons
  * (any host thread: PyTorch runs backward on an autograd worker thread) records `event` (a cudaEvent_t) on its stream once all 17 parameter gradients are enqueued, i.e.
  * before the dL/dF GEMM, so the caller's gradient all-reduce can overlap that last kernel.  NULL clears it. */
 void dic_set_grads_ready_event(void* event);
+/* Bucketed form of the same hook (any of the three may be NULL).  The gradients live in one flat buffer in
+ * dic_params order; the next backward records
+ *   ev_linear  once lin_w / lin_b (the LAST two tensors) are final -- before the backward time loop starts,
+ *   ev_middle  once everything but enc_att_w / enc_att_b (the FIRST two tensors) is final,
+ *   ev_all     once all 17 are final (before the dL/dF GEMM, which then leaves some SMs to the all-reduce). */
+void dic_set_grads_ready_events(void* ev_linear, void* ev_middle, void* ev_all);
 
 /* ---- fused caption-loss head ----------------------------------------------
  * Replaces the caller-side loss of the training loop (depth_train.py:210-216 / :530-532):
