@@ -319,7 +319,7 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
         hd.h = reinterpret_cast<const bf16*>(X + d.E + d.D); hd.h_ld = (long long)XW;
         hd.Wdb = reinterpret_cast<const bf16*>(pk.Wdb(d)); hd.bias_db = pk.bias_db();
         hd.HP = HPt; hd.a = a; hd.rows = n;
-        DIC_TRY(launch_attn_head(hd, sst));
+        DIC_TRY(launch_attn_head(hd, 1, sst));
         a.skip_alpha = 1;
       }
       DIC_TRY(launch_attn_step<ST>(a, n, 1, sst));
@@ -726,7 +726,7 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
         hd.h = reinterpret_cast<const bf16*>(X + E + D); hd.h_ld = XW;
         hd.Wdb = reinterpret_cast<const bf16*>(pk.Wdb(d)); hd.bias_db = pk.bias_db();
         hd.HP = HPs; hd.a = a; hd.rows = Rs;
-        DIC_TRY(launch_attn_head(hd, sst));
+        DIC_TRY(launch_attn_head(hd, K, sst));
         a.skip_alpha = 1;
       }
       DIC_TRY(launch_attn_step<ST>(a, Bs, K, sst));
@@ -882,6 +882,10 @@ int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void*
   add(p->w_hh, d.H, base + lay.Whdb, d.H, bf, 4 * d.H, d.H);
   add(p->dec_att_w, d.H, base + lay.Whdb + (size_t)4 * d.H * d.H * es, d.H, bf, d.A, d.H);
   add(p->fbeta_w, d.H, base + lay.Whdb + (size_t)(4 * d.H + d.A) * d.H * es, d.H, bf, d.D, d.H);
+  // Whdb0 = [W_hh ; 0 ; W_beta]
+  add(p->w_hh, d.H, base + lay.Whdb0, d.H, bf, 4 * d.H, d.H);
+  DIC_CUDA(cudaMemsetAsync(base + lay.Whdb0 + (size_t)4 * d.H * d.H * es, 0, (size_t)d.A * d.H * es, st));
+  add(p->fbeta_w, d.H, base + lay.Whdb0 + (size_t)(4 * d.H + d.A) * d.H * es, d.H, bf, d.D, d.H);
   add(p->w_ih, d.E + d.D, base + lay.Wg, XW, bf, 4 * d.H, d.E + d.D);
   add(p->w_hh, d.H, base + lay.Wg + (size_t)(d.E + d.D) * es, XW, bf, 4 * d.H, d.H);
   if (bf && d.H % kGlUnits == 0 && gates_lstm_enabled()) {     // gate-interleaved copy for the cluster-fused LSTM step

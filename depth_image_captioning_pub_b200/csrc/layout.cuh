@@ -18,13 +18,14 @@ struct Carver {
 //   Wenc  [A,D]            attention.encoder_att.weight
 //   Whdb  [4H+A+D, H]      rows: W_hh | W_dec | W_beta  (backward: dh = G . Whdb)
 //         Wdb = Whdb + 4H*H  -> [A+D, H] forward h-projection (att2 | beta)
+//   Whdb0 [4H+A+D, H]      rows: W_hh | 0 | W_beta: the part of dh that does not wait for the attention backward
 //   Wg    [4H, E+D+H]      [W_ih | W_hh]: gates = [emb|zg|h] . Wg^T
 //   Wgp   [4H, E+D+H]      Wg with rows interleaved per tile of U = 32 units: row (u/U)*4U + gate*U + u%U = Wg row gate*H + u
 //   Winit [2H,D], Wout [V,H], Emb [V,E]
 //   fp32: b_enc[A], bias_db[A+D] = b_dec|b_beta, bias_g[4H] = b_ih+b_hh, b_init[2H], b_out[V],
 //         w_full[A], b_full[1]
 struct PackLayout {
-  size_t Wenc, Whdb, Wg, Wgp, Winit, Wout, Emb;
+  size_t Wenc, Whdb, Whdb0, Wg, Wgp, Winit, Wout, Emb;
   size_t b_enc, bias_db, bias_g, b_init, b_out, w_full, b_full;
   size_t bytes;
   int es;  // element size of ST
@@ -34,6 +35,7 @@ struct PackLayout {
     const size_t XW = (size_t)d.E + d.D + d.H;
     Wenc = c.take((size_t)d.A * d.D * es);
     Whdb = c.take((size_t)(4 * d.H + d.A + d.D) * d.H * es);
+    Whdb0 = c.take((size_t)(4 * d.H + d.A + d.D) * d.H * es);   // Whdb with the W_dec rows zeroed (off-chain dh GEMM)
     Wg = c.take((size_t)4 * d.H * XW * es);
     Wgp = c.take((size_t)4 * d.H * XW * es);   // gate-interleaved copy of Wg (gates_lstm.cuh)
     Winit = c.take((size_t)2 * d.H * d.D * es);
@@ -57,6 +59,8 @@ struct Pack {
   Pack(const void* p, const dic_dims& d, int dtype) : base(reinterpret_cast<const char*>(p)), lay(d, dtype) {}
   const void* Wenc() const { return base + lay.Wenc; }
   const void* Whdb() const { return base + lay.Whdb; }
+  const void* Whdb0() const { return base + lay.Whdb0; }
+  const void* Wdec(const dic_dims& d) const { return base + lay.Whdb + (size_t)4 * d.H * d.H * lay.es; }
   const void* Wdb(const dic_dims& d) const { return base + lay.Whdb + (size_t)4 * d.H * d.H * lay.es; }
   const void* Wg() const { return base + lay.Wg; }
   const void* Wgp() const { return base + lay.Wgp; }
@@ -117,7 +121,7 @@ struct TrainLayout {
     dlogits16 = c.take(dtype == DIC_BF16 ? TB * d.V * 2 : 16);   // bf16 copy of d_logits (GEMM operand)
     dal_part = c.take(sizeof(float) * (size_t)((d.D + 255) / 256) * B * d.L);   // per-chunk dalpha partials
     h0 = c.take(sizeof(float) * B * d.H);
-    dh_part = c.take(sizeof(float) * kDhSplitsMax * B * d.H);
+    dh_part = c.take(sizeof(float) * (kDhSplitsMax + 1) * B * d.H);   // + the datt2 . W_dec slot of the small kernel
     dF32 = c.take(sizeof(float) * (size_t)B * d.L * d.D);   // fp32 dL/dF accumulator when annotations are bf16
     Lp = (d.L + 7) & ~7;
     alpha16 = c.take(TB * Lp * 2);     // bf16 alpha [B,T,Lp]: A operand of the fused dL/dF GEMM

@@ -270,7 +270,7 @@ struct PackJob {
   int gate_H;              // > 0: destination row of source row q*gate_H + u is (u/U)*4U + q*U + u%U, U = gate_U
   int gate_U;
 };
-constexpr int kMaxPackJobs = 20;
+constexpr int kMaxPackJobs = 24;
 struct PackJobs {
   PackJob j[kMaxPackJobs];
   int n;
