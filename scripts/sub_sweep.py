@@ -20,6 +20,8 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--decode-batch", type=int, default=128)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--subs", default="1,2,3,4,6,8")
+ap.add_argument("--no-decode", action="store_true")
+ap.add_argument("--tag", default="")
 args = ap.parse_args()
 L, D, A, E, H, V, T = bench.L, bench.D, bench.A, bench.E, bench.H, bench.V, bench.T
 dev = torch.device("cuda", 0)
@@ -62,8 +64,11 @@ subs = [int(x) for x in args.subs.split(",")]
 for s in subs:
     lib.dic_set_substreams(s)
     ms = timed(train_step, args.steps)
-    print(f"train  B={B} substreams={s}: {ms:.3f} ms/step  {B * T / ms * 1e3:.0f} tokens/s", flush=True)
+    print(f"{args.tag}train  B={B} substreams={s}: {ms:.3f} ms/step  {B * T / ms * 1e3:.0f} tokens/s", flush=True)
 
+if args.no_decode:
+    lib.dic_set_substreams(0)
+    sys.exit(0)
 m.eval()
 m.cache_packed_weights = True
 voc = O.synthetic_vocab(V)
