@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "decode.cuh"
 #include "dfeat_tc.cuh"
+#include "dp_allreduce.cuh"
 #include "gemm_generic.cuh"
 #include "gemm_tc.cuh"
 #include "gates_lstm.cuh"
@@ -849,6 +850,27 @@ void dic_set_grads_ready_events(void* ev_linear, void* ev_middle, void* ev_all) 
   g_grads_lin_event.store(reinterpret_cast<cudaEvent_t>(ev_linear));
   g_grads_mid_event.store(reinterpret_cast<cudaEvent_t>(ev_middle));
   g_grads_ready_event.store(reinterpret_cast<cudaEvent_t>(ev_all));
+}
+
+size_t dic_dp_flag_bytes(void) { return kDpFlagWords * sizeof(uint32_t); }
+
+int dic_dp_allreduce(int world, int rank, void* const* bufs, void* const* flags, void* multicast, long long n_floats,
+                     float scale, unsigned int epoch, int blocks, void* stream) {
+  if (!bufs || !flags) DIC_FAIL(-4, "dp_allreduce: null pointer table");
+  if (world < 1 || world > kDpMaxRanks) DIC_FAIL(-4, "dp_allreduce: world size %d not in 1..%d", world, kDpMaxRanks);
+  if (n_floats <= 0 || n_floats % (4LL * world)) DIC_FAIL(-4, "dp_allreduce: %lld floats are not a multiple of 4 x world", n_floats);
+  if (epoch == 0) DIC_FAIL(-4, "dp_allreduce: epochs count from 1 (the flag words start at 0)");
+  DpArgs p;
+  memset(&p, 0, sizeof(p));
+  for (int r = 0; r < world; ++r) {
+    if (!bufs[r] || !flags[r]) DIC_FAIL(-4, "dp_allreduce: null buffer / flag pointer of rank %d", r);
+    if (reinterpret_cast<uintptr_t>(bufs[r]) & 15) DIC_FAIL(-4, "dp_allreduce: buffer of rank %d is not 16-byte aligned", r);
+    p.bufs[r] = reinterpret_cast<float*>(bufs[r]);
+    p.flags[r] = reinterpret_cast<uint32_t*>(flags[r]);
+  }
+  p.mc = reinterpret_cast<float*>(multicast);
+  p.rank = rank; p.world = world; p.n4 = n_floats / 4; p.scale = scale; p.epoch = epoch;
+  return launch_dp_allreduce(p, blocks, reinterpret_cast<cudaStream_t>(stream));
 }
 
 void dic_set_substreams(int n) { g_sub_override.store(n < 0 ? 0 : (n > kMaxSub ? kMaxSub : n)); }

@@ -77,6 +77,7 @@ class _DecoderBase(nn.Module):
             eng = Engine(L, D, A, E, H, V, self.precision, device)
             self._engines[key] = eng
         eng.use_flat_grads = bool(getattr(self, "flat_grads", False))
+        eng.flat_alloc = getattr(self, "flat_alloc", None)
         return eng
 
     def _check_feats(self, features, depth_features):

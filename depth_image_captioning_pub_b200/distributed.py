@@ -31,6 +31,50 @@ def shard_sorted_batch(lengths: Sequence[int], rank: int, world: int) -> List[in
     return list(range(rank, len(lengths), world))
 
 
+class PeerBuffer:
+    """A flat fp32 buffer in peer-visible (symmetric) memory + the flag block of the library's NVLink
+    all-reduce (csrc/dp_allreduce.cuh, dic_dp_allreduce).  Collective: every rank of `group` must construct it
+    at the same point with the same n."""
+
+    def __init__(self, n: int, device: torch.device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        lib = _lib.load()
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("the NVLink all-reduce serves one node (<= 8 ranks)")
+        quantum = 4 * self.world
+        self.n = n
+        self.n_pad = (n + quantum - 1) // quantum * quantum
+        flag_words = int(lib.dic_dp_flag_bytes()) // 4
+        self.base = symm.empty(self.n_pad + flag_words, dtype=torch.float32, device=device)
+        self.base.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.base, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._bufs = (C.c_void_p * self.world)(*ptrs)
+        self._flags = (C.c_void_p * self.world)(*[p + 4 * self.n_pad for p in ptrs])
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        import os
+        self.multicast = mc if os.environ.get("DIC_DP_MULTIMEM", "0") == "1" else 0
+        self.flat = self.base[:n]
+        self.epoch = 0
+        self.blocks = int(os.environ.get("DIC_DP_BLOCKS", "20"))      # = the SMs the dL/dF GEMM leaves free (kAllReduceSms)
+        self._lib = lib
+        dist.barrier(group)          # every rank's flags are zero before anyone's first all-reduce can write to them
+
+    def all_reduce(self, average: bool = True) -> None:
+        """In place on the current stream: flat <- (sum over ranks) (/ world)."""
+        from . import _lib
+        self.epoch += 1
+        _lib.check(self._lib.dic_dp_allreduce(
+            self.world, self.rank, self._bufs, self._flags, self.multicast, self.n_pad,
+            (1.0 / self.world) if average else 1.0, self.epoch, self.blocks, _lib.stream_ptr(self.base.device)))
+
+
 class FlatGradAllReduce:
     """One flat fp32 buffer for all gradients -> a single (NCCL) all-reduce per step.
 
@@ -39,13 +83,29 @@ class FlatGradAllReduce:
     runs in place: no gather / scatter copies.  Parameters whose gradients are not in that buffer
     (extra trainable tensors, or a step where the aliasing did not happen) take the copy path."""
 
-    def __init__(self, params: Sequence[torch.Tensor], module=None):
+    def __init__(self, params: Sequence[torch.Tensor], module=None, mode: Optional[str] = None, group=None):
+        """mode: "p2p_overlap" (default on NCCL process groups: the library's own all-reduce over NVLink peer
+        memory, dic_dp_allreduce, on a side stream next to the dL/dF GEMM, which leaves it 20 SMs), "p2p" (the same
+        kernel after the backward on the main stream), "nccl" (three bucketed ncclAllReduce calls on a side stream),
+        "none" (no exchange; diagnosis).  Measured on 2 B200 (profiles/r02_dp_modes_n2.txt), 2.825 ms/step alone:
+        none 2.853, p2p 2.871, p2p_overlap 2.842, nccl 2.876 ms/step."""
+        import os
         self.params = [p for p in params]
         self.module = module
+        self.group = group
         self._ready = None
         self._comm = None
+        self._peer: Optional[PeerBuffer] = None
+        if mode is None:
+            mode = os.environ.get("DIC_DP_MODE", "")
+        if not mode:
+            nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+            mode = "p2p_overlap" if (nccl and module is not None) else "nccl"
+        self.mode = mode
         if module is not None:
             module.flat_grads = True
+            if mode.startswith("p2p"):
+                module.flat_alloc = self._alloc_peer
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -55,6 +115,19 @@ class FlatGradAllReduce:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
 
+    def _alloc_peer(self, n: int, device: torch.device):
+        """Engine hook: the flat gradient buffer comes from peer-visible memory.  A failure to set that up (no
+        peer access, symmetric memory unavailable) is reported once and the NCCL path takes over."""
+        try:
+            self._peer = PeerBuffer(n, device, self.group)
+        except Exception as e:          # noqa: BLE001  (every rank sees the same failure: the set-up is collective)
+            import warnings
+            warnings.warn(f"NVLink all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+            self._peer = None
+            self.mode = "nccl"
+            return None
+        return self._peer.flat
+
     def arm(self) -> None:
         """Call right before loss.backward(): the library then records three events while it enqueues the
         backward -- vocabulary-projection gradients final (before the time loop), everything but the
@@ -62,6 +135,8 @@ class FlatGradAllReduce:
         slices of the flat buffer on a side stream from those points, overlapping the rest of backward."""
         if self.module is None or not torch.cuda.is_available():
             return
+        if self.mode in ("p2p", "plain"):
+            return                                  # the reduce follows the backward on the same stream
         from . import _lib
         if self._ready is None:
             self._ready = [torch.cuda.Event() for _ in range(3)]
@@ -69,14 +144,15 @@ class FlatGradAllReduce:
                 ev.record()                         # instantiates the underlying cudaEvent_t
             self._comm = torch.cuda.Stream()
         self._armed = True
-        _lib.load().dic_set_grads_ready_events(*[ev.cuda_event for ev in self._ready])
+        if self.mode == "p2p_overlap":
+            _lib.load().dic_set_grads_ready_events(None, None, self._ready[2].cuda_event)
+        else:
+            _lib.load().dic_set_grads_ready_events(*[ev.cuda_event for ev in self._ready])
 
-    def _buckets(self, flat: torch.Tensor):
+    def _buckets(self, flat: torch.Tensor, offsets):
         """(linear, middle, encoder_att) slices of the flat buffer, in the order their events fire."""
-        sizes = [p.numel() for p in self.params]
-        n = flat.numel()
-        head, tail = sizes[0] + sizes[1], sizes[-2] + sizes[-1]
-        return [flat[n - tail:], flat[head:n - tail], flat[:head]]
+        head, tail = offsets[2], offsets[-2]
+        return [flat[tail:], flat[head:tail], flat[:head]]
 
     def _in_place(self, average: bool, group) -> bool:
         m = self.module
@@ -98,11 +174,22 @@ class FlatGradAllReduce:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
                 if average:
                     t.mul_(1.0 / dist.get_world_size(group))
-        if getattr(self, "_armed", False) and e.grad_flat.is_cuda and len(self.params) >= 5:
+        peer = self._peer
+        if peer is not None and peer.flat.data_ptr() == e.grad_flat.data_ptr() and self.mode.startswith("p2p"):
+            if self.mode == "p2p_overlap" and getattr(self, "_armed", False):
+                self._armed = False
+                main = torch.cuda.current_stream()
+                with torch.cuda.stream(self._comm):
+                    self._comm.wait_event(self._ready[2])
+                    peer.all_reduce(average)
+                main.wait_stream(self._comm)
+            else:
+                peer.all_reduce(average)
+        elif getattr(self, "_armed", False) and e.grad_flat.is_cuda and len(self.params) >= 5:
             self._armed = False
             main = torch.cuda.current_stream()
             with torch.cuda.stream(self._comm):
-                for ev, part in zip(self._ready, self._buckets(e.grad_flat)):
+                for ev, part in zip(self._ready, self._buckets(e.grad_flat, e.grad_offsets)):
                     self._comm.wait_event(ev)       # recorded by the library inside this step's backward
                     reduce(part)
             main.wait_stream(self._comm)                # the optimizer step comes after the all-reduce
@@ -111,6 +198,8 @@ class FlatGradAllReduce:
         return True
 
     def __call__(self, average: bool = True, group=None) -> None:
+        if self.mode == "none":          # diagnosis only: no exchange at all (what does being one of N ranks cost?)
+            return
         if self._in_place(average, group):
             return
         world = dist.get_world_size(group)

@@ -159,14 +159,25 @@ class Engine:
     def _flat_grad_views(self, param_shapes) -> List[torch.Tensor]:
         """Fresh view tensors into the persistent flat gradient buffer (autograd's AccumulateGrad takes
         them over as .grad without a copy, so p.grad aliases the flat buffer after backward)."""
-        n = sum(int(np.prod(s)) for s in param_shapes)
-        if self.grad_flat is None or self.grad_flat.numel() != n:
-            self.grad_flat = torch.empty(n, dtype=torch.float32, device=self.device)
-        views, o = [], 0
+        # every tensor starts on a 256-byte boundary: the kernels' 16-byte stores / vector red.add / AdamW's float4
+        # path need aligned bases (full_att.bias has ONE element: packed back to back, every tensor behind it sat
+        # on a 4-byte boundary and took the scalar paths -- 0.1 ms per step, profiles/r02_dp_timeline_*.txt)
+        ALIGN = 64
+        offs, o = [], 0
         for s in param_shapes:
-            k = int(np.prod(s))
-            views.append(self.grad_flat[o:o + k].view(s))
-            o += k
+            offs.append(o)
+            o += (int(np.prod(s)) + ALIGN - 1) // ALIGN * ALIGN
+        n = o
+        if self.grad_flat is None or self.grad_flat.numel() != n:
+            # a data-parallel wrapper may supply the buffer (peer-visible memory for the NVLink all-reduce)
+            alloc = getattr(self, "flat_alloc", None)
+            self.grad_flat = alloc(n, self.device) if alloc is not None else None
+            if self.grad_flat is None:
+                self.grad_flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grad_offsets = offs
+        views = []
+        for s, o in zip(param_shapes, offs):
+            views.append(self.grad_flat[o:o + int(np.prod(s))].view(s))
         # keep no reference to the views: AccumulateGrad only takes a gradient over without a copy when
         # nobody else holds it
         self._grad_ptrs = {v.data_ptr() for v in views}

@@ -166,6 +166,19 @@ void dic_set_grads_ready_event(void* event);
  *   ev_all     once all 17 are final (before the dL/dF GEMM, which then leaves some SMs to the all-reduce). */
 void dic_set_grads_ready_events(void* ev_linear, void* ev_middle, void* ev_all);
 
+/* ---- data-parallel gradient all-reduce over NVLink peer memory ------------------------------
+ * The one exchange step of the path.  The reference has no distributed code (config.py:68 pins 'cuda:0'); this
+ * replaces the NCCL all-reduce a DistributedDataParallel wrapper would issue after depth_train.py:219 (loss.backward()).
+ * Every rank passes the SAME tables: bufs[r] / flags[r] = rank r's flat fp32 gradient buffer / flag block
+ * (dic_dp_flag_bytes() bytes, zero before the first call) as mapped into THIS process (peer-visible memory, e.g.
+ * torch.distributed._symmetric_memory buffer_ptrs); multicast = NVLS multicast mapping of the buffers or NULL.
+ * In place: buf <- scale * sum_r buf_r on every rank, summed in rank order (bit-identical on all ranks).
+ * n_floats: a multiple of 4*world.  epoch: 1, 2, 3, ... the same on every rank for the same call.  blocks: CTAs
+ * to use (<= 148; 0 = default).  One kernel on `stream`; no host synchronisation. */
+size_t dic_dp_flag_bytes(void);
+int dic_dp_allreduce(int world, int rank, void* const* bufs, void* const* flags, void* multicast,
+                     long long n_floats, float scale, unsigned int epoch, int blocks, void* stream);
+
 /* ---- fused caption-loss head ----------------------------------------------
  * Replaces the caller-side loss of the training loop (depth_train.py:210-216 / :530-532):
  *   loss = cross_entropy(packed logits, packed targets, ignore_index, mean over non-ignored)

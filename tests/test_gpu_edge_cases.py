@@ -142,7 +142,8 @@ def test_flat_grad_buffer_aliases_param_grads(cuda_device):
         assert lo <= p.grad.data_ptr() < hi, k
         # (weight gradients use atomic split-K: equal up to the fp32 summation order)
         assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7 + 1e-5 * float(q.grad.abs().max())), k
-        n += p.numel()
+        assert p.grad.data_ptr() % 256 == 0, k      # every tensor on its own 256-byte boundary (vector stores / red.add)
+        n += (p.numel() + 63) // 64 * 64
     assert n == eng.grad_flat.numel()
     # a second step re-uses the buffer after zero_grad(set_to_none=True)
     got.zero_grad(set_to_none=True)
