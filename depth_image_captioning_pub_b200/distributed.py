@@ -59,7 +59,11 @@ class PeerBuffer:
         self._flags = (C.c_void_p * self.world)(*[p + 4 * self.n_pad for p in ptrs])
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         import os
-        self.multicast = mc if os.environ.get("DIC_DP_MULTIMEM", "0") == "1" else 0
+        # NVLS (multimem.ld_reduce / multimem.st through the switch) wins from 4 ranks up, plain peer loads below:
+        # 2 GPUs 48 us vs 70 us per 19.3 MB, 8 GPUs 80 us vs 66 us (profiles/r02_dp_allreduce_bench_n{2,8}.txt);
+        # 8-GPU step 2.853 ms with it, 2.880 without, 2.857 with no exchange at all (profiles/r02_dp_modes_n8.txt)
+        want = os.environ.get("DIC_DP_MULTIMEM", "auto")
+        self.multicast = mc if (want == "1" or (want == "auto" and self.world >= 4)) else 0
         self.flat = self.base[:n]
         self.epoch = 0
         self.blocks = int(os.environ.get("DIC_DP_BLOCKS", "20"))      # = the SMs the dL/dF GEMM leaves free (kAllReduceSms)
