@@ -4,6 +4,7 @@
 #include "attention_bulk.cuh"
 #include "attention_mma.cuh"
 #include "attn_head.cuh"
+#include "beam_fused.cuh"
 #include "common.cuh"
 #include "decode.cuh"
 #include "dfeat_tc.cuh"
@@ -745,6 +746,25 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       DIC_TRY(lstm_step<ST>(d, pk, X, XW, Rs, R, gp, l, sst));
 
       float* lg = logits_out ? logits_out + ((size_t)t * R + r0) * V : logits_ws + r0 * V;
+      if (beam && is_bf16 && !logits_out && !lse_out && beam_fused_eligible(H, V, K, Rs)) {
+        // vocabulary projection + log-sum-exp + per-row top-K in one tcgen05 kernel, merge + reorder in one more
+        // (beam_fused.cuh)
+        int32_t* back_t = back_ws + (size_t)t * R + r0;
+        int32_t* tok_t = tok_ws + (size_t)t * R + r0;
+        BeamMergeArgs mg;
+        memset(&mg, 0, sizeof(mg));
+        mg.scores = sc[t & 1] + r0; mg.finished = fin[t & 1] + r0;
+        mg.new_scores = sc[(t + 1) & 1] + r0; mg.back = back_t; mg.tok = tok_t; mg.new_finished = fin[(t + 1) & 1] + r0;
+        mg.h_tmp = h_tmp + r0 * H; mg.c_tmp = c_tmp + r0 * H; mg.emb = pk.Emb();
+        mg.Xnext = Xn; mg.x_row = XW; mg.col_h = E + D; mg.c = c + r0 * H;
+        mg.end_id = end_id; mg.E = E; mg.H = H;
+        float* bstats = reinterpret_cast<float*>(ws + lay.bstats) + r0 * 2 * cdiv(V, kBfNB);
+        DIC_TRY(launch_beam_fused<ST>(h_tmp + r0 * H, pk.Wout(), pk.b_out(), lg, bstats, mg, Rs, V, K, sst));
+        if (step_scores_out)
+          DIC_CUDA(cudaMemcpyAsync(step_scores_out + (size_t)t * R + r0, sc[(t + 1) & 1] + r0, sizeof(float) * Rs,
+                                   cudaMemcpyDeviceToDevice, sst));
+        continue;
+      }
       const ST* hsrc = beam ? h_tmp + r0 * H : Xn + E + D;
       GemmArgs g = gemm_args_nt(hsrc, is_bf16, beam ? H : XW, pk.Wout(), is_bf16, H, lg, 0, V, Rs, V, H, pk.b_out());
       g.tag = 5;
