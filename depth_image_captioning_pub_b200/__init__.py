@@ -12,10 +12,11 @@ from .decoders import (CD_RNNDecoderWithHardAttention, CD_RNNDecoderWithSoftAtte
                        MD_RNNDecoderWithHardAttention, MD_RNNDecoderWithSoftAttention,
                        RNNDecoderWithHardAttention, RNNDecoderWithSoftAttention)
 
+from .encoders import Depth_CNN_endoder  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 
 __all__ = [
-    "FusedAdamW",
+    "FusedAdamW", "Depth_CNN_endoder",
     "DicError", "Gumbel_softmax", "Hard_Attention", "Soft_Attention",
     "CD_RNNDecoderWithHardAttention", "CD_RNNDecoderWithSoftAttention",
     "MD_RNNDecoderWithHardAttention", "MD_RNNDecoderWithSoftAttention",

@@ -98,6 +98,9 @@ PROTOTYPES = {
     "dic_set_substreams": (None, [_I]),
     "dic_set_grads_ready_event": (None, [_P]),
     "dic_set_grads_ready_events": (None, [_P, _P, _P]),
+    "dic_depth_encoder_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "dic_depth_encoder_forward": (_I, [_I, _I, _I, _I, _I, _P, _P, _F, _F, _P, _I, _P, _SZ, _P]),
+    "dic_depth_encoder_backward": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _SZ, _P]),
     "dic_dp_flag_bytes": (C.c_size_t, []),
     "dic_dp_allreduce": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_longlong, C.c_float, C.c_uint, C.c_int, _P]),
     "dic_trace_start": (_I, [_P, C.c_uint]),

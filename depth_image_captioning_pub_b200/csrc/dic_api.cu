@@ -7,6 +7,7 @@
 #include "beam_fused.cuh"
 #include "common.cuh"
 #include "decode.cuh"
+#include "depth_encoder.cuh"
 #include "dfeat_tc.cuh"
 #include "dp_allreduce.cuh"
 #include "gemm_generic.cuh"
@@ -817,6 +818,187 @@ using namespace dic;
 // =============================================================================================
 // extern "C"
 // =============================================================================================
+
+// =============================================================================================
+// depth CNN encoder (depth_encoder.cuh)
+// =============================================================================================
+static int enc_check(int B, int Hi, int Wi, int dtype) {
+  if (dtype != DIC_F32 && dtype != DIC_BF16) DIC_FAIL(-2, "depth encoder: dtype must be DIC_F32 or DIC_BF16");
+  if (B < 1 || Hi < 7 || Wi < 7) DIC_FAIL(-2, "depth encoder: bad input shape [%d, %d, %d]", B, Hi, Wi);
+  const EncGeom g(B, Hi, Wi);
+  if (g.P2h != 7 || g.P2w != 7)
+    DIC_FAIL(-2, "depth encoder: the last feature map is %d x %d; AdaptiveAvgPool2d(14) is built as the exact 2 x 2 "
+             "replication of a 7 x 7 map (224 x 224 depth images, depth_models.py:18-32)", g.P2h, g.P2w);
+  return 0;
+}
+
+template <typename ST>
+static int enc_bn_stage(const float* X, size_t M, int C, int slot, char* ws, const EncLayout& lay, int training,
+                        float momentum, float eps, float* rmean, float* rvar, const float** mean_o, const float** invstd_o,
+                        cudaStream_t st) {
+  double* sum = reinterpret_cast<double*>(ws + lay.stats) + (size_t)slot * 2 * 2048;
+  double* sumsq = sum + 2048;
+  float* mean = reinterpret_cast<float*>(ws + lay.mean) + (size_t)slot * 2048;
+  float* invstd = reinterpret_cast<float*>(ws + lay.invstd) + (size_t)slot * 2048;
+  if (training) {
+    DIC_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * 2048, st));
+    const int rpb = 256;
+    dim3 grid(cdiv(C, 256), (unsigned)((M + rpb - 1) / rpb));
+    enc_stats_kernel<<<grid, 256, 0, st>>>(X, M, C, rpb, sum, sumsq);
+    DIC_LAUNCH_CHECK();
+  }
+  enc_bn_finalize_kernel<<<cdiv(C, 256), 256, 0, st>>>(sum, sumsq, (double)M, C, training, momentum, eps, rmean, rvar,
+                                                       mean, invstd);
+  DIC_LAUNCH_CHECK();
+  *mean_o = mean; *invstd_o = invstd;
+  return 0;
+}
+
+template <typename ST>
+static int depth_encoder_forward_impl(int training, const EncGeom& g, const float* imgs, const dic_enc_params& p,
+                                      float momentum, float eps, void* feats, int feat_dtype, char* ws, cudaStream_t st) {
+  const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
+  const int is_bf16 = sizeof(ST) == 2;
+  const EncLayout lay(g, dtype);
+  ST* col1 = reinterpret_cast<ST*>(ws + lay.col1);
+  float* out1 = reinterpret_cast<float*>(ws + lay.out1);
+  ST* p1 = reinterpret_cast<ST*>(ws + lay.p1);
+  ST* col2 = reinterpret_cast<ST*>(ws + lay.col2);
+  float* out2 = reinterpret_cast<float*>(ws + lay.out2);
+  ST* p2 = reinterpret_cast<ST*>(ws + lay.p2);
+  float* out3 = reinterpret_cast<float*>(ws + lay.out3);
+  ST* w1p = reinterpret_cast<ST*>(ws + lay.w1p);
+  ST* w2p = reinterpret_cast<ST*>(ws + lay.w2p);
+  ST* w3p = reinterpret_cast<ST*>(ws + lay.w3p);
+  const int K2 = 9 * g.C1;
+  enc_pack_w_kernel<ST><<<enc_grid((size_t)g.C1 * g.K1p), 256, 0, st>>>(p.conv1_w, w1p, g.C1, 1, 49, g.K1p);
+  enc_pack_w_kernel<ST><<<enc_grid((size_t)g.C2 * K2), 256, 0, st>>>(p.conv2_w, w2p, g.C2, g.C1, 9, K2);
+  enc_pack_w_kernel<ST><<<enc_grid((size_t)g.C3 * g.C2), 256, 0, st>>>(p.conv3_w, w3p, g.C3, g.C2, 1, g.C2);
+  DIC_LAUNCH_CHECK();
+  const float *mean, *invstd;
+  // stage 1
+  enc_im2col_kernel<float, ST><<<enc_grid(g.M1() * g.K1p), 256, 0, st>>>(imgs, col1, g.B, g.Hi, g.Wi, 1, 7, 3, g.H1, g.W1, g.K1p);
+  DIC_LAUNCH_CHECK();
+  DIC_TRY(gemm(gemm_args_nt(col1, is_bf16, g.K1p, w1p, is_bf16, g.K1p, out1, 0, g.C1, (int)g.M1(), g.C1, g.K1p, p.conv1_b), st));
+  DIC_TRY(enc_bn_stage<ST>(out1, g.M1(), g.C1, 0, ws, lay, training, momentum, eps, p.bn1_mean, p.bn1_var, &mean, &invstd, st));
+  enc_bn_relu_pool_kernel<ST><<<enc_grid((size_t)g.B * g.P1h * g.P1w * g.C1), 256, 0, st>>>(out1, mean, invstd, p.bn1_w, p.bn1_b, p1,
+                                                                                          g.B, g.H1, g.W1, g.C1, 3, 1);
+  DIC_LAUNCH_CHECK();
+  // stage 2
+  enc_im2col_kernel<ST, ST><<<enc_grid(g.M2() * K2), 256, 0, st>>>(p1, col2, g.B, g.P1h, g.P1w, g.C1, 3, 1, g.H2, g.W2, K2);
+  DIC_LAUNCH_CHECK();
+  DIC_TRY(gemm(gemm_args_nt(col2, is_bf16, K2, w2p, is_bf16, K2, out2, 0, g.C2, (int)g.M2(), g.C2, K2, p.conv2_b), st));
+  DIC_TRY(enc_bn_stage<ST>(out2, g.M2(), g.C2, 1, ws, lay, training, momentum, eps, p.bn2_mean, p.bn2_var, &mean, &invstd, st));
+  enc_bn_relu_pool_kernel<ST><<<enc_grid(g.M3() * g.C2), 256, 0, st>>>(out2, mean, invstd, p.bn2_w, p.bn2_b, p2, g.B, g.H2, g.W2,
+                                                                       g.C2, 3, 1);
+  DIC_LAUNCH_CHECK();
+  // stage 3: 1 x 1 convolution, then BN + ReLU + 2 x 2 replication straight into the annotation tensor
+  DIC_TRY(gemm(gemm_args_nt(p2, is_bf16, g.C2, w3p, is_bf16, g.C2, out3, 0, g.C3, (int)g.M3(), g.C3, g.C2, p.conv3_b), st));
+  DIC_TRY(enc_bn_stage<ST>(out3, g.M3(), g.C3, 2, ws, lay, training, momentum, eps, p.bn3_mean, p.bn3_var, &mean, &invstd, st));
+  if (feat_dtype == DIC_BF16)
+    enc_bn_relu_pool_kernel<bf16><<<enc_grid(g.M3() * g.C3), 256, 0, st>>>(out3, mean, invstd, p.bn3_w, p.bn3_b,
+                                                                           reinterpret_cast<bf16*>(feats), g.B, g.P2h, g.P2w,
+                                                                           g.C3, 1, 2);
+  else
+    enc_bn_relu_pool_kernel<float><<<enc_grid(g.M3() * g.C3), 256, 0, st>>>(out3, mean, invstd, p.bn3_w, p.bn3_b,
+                                                                            reinterpret_cast<float*>(feats), g.B, g.P2h, g.P2w,
+                                                                            g.C3, 1, 2);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename ST>
+static int depth_encoder_backward_impl(const EncGeom& g, const dic_enc_params& p, const void* d_feats, int feat_dtype,
+                                       const dic_enc_params& gr, char* ws, cudaStream_t st) {
+  const int dtype = sizeof(ST) == 2 ? DIC_BF16 : DIC_F32;
+  const int is_bf16 = sizeof(ST) == 2;
+  const EncLayout lay(g, dtype);
+  ST* col1 = reinterpret_cast<ST*>(ws + lay.col1);
+  float* out1 = reinterpret_cast<float*>(ws + lay.out1);
+  ST* col2 = reinterpret_cast<ST*>(ws + lay.col2);
+  float* out2 = reinterpret_cast<float*>(ws + lay.out2);
+  ST* p2 = reinterpret_cast<ST*>(ws + lay.p2);
+  float* out3 = reinterpret_cast<float*>(ws + lay.out3);
+  ST* w2p = reinterpret_cast<ST*>(ws + lay.w2p);
+  ST* w3p = reinterpret_cast<ST*>(ws + lay.w3p);
+  float* dy3 = reinterpret_cast<float*>(ws + lay.dy3);
+  float* dy2 = reinterpret_cast<float*>(ws + lay.dy2);
+  float* dy1 = reinterpret_cast<float*>(ws + lay.dy1);
+  bf16* dx16 = reinterpret_cast<bf16*>(ws + lay.dx16);
+  float* dp2 = reinterpret_cast<float*>(ws + lay.dp2);
+  float* dcol2 = reinterpret_cast<float*>(ws + lay.dcol2);
+  float* dp1 = reinterpret_cast<float*>(ws + lay.dp1);
+  float* dwp = reinterpret_cast<float*>(ws + lay.dwp);
+  double* stats = reinterpret_cast<double*>(ws + lay.stats);
+  const float* mean = reinterpret_cast<const float*>(ws + lay.mean);
+  const float* invstd = reinterpret_cast<const float*>(ws + lay.invstd);
+  const int K2 = 9 * g.C1;
+  DIC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 3 * 2 * 2048, st));
+
+  // one stage: route dY through replication / max-pool / ReLU, reduce, apply the BN backward
+  auto stage = [&](auto gt_tag, const void* dY, const float* X, float* dy, int slot, int H, int W, int C, int P, int R,
+                   const float* gamma, const float* beta, float* dgamma, float* dbeta) -> int {
+    using GT = decltype(gt_tag);
+    const size_t M = (size_t)g.B * H * W;
+    if (H % P || W % P) DIC_CUDA(cudaMemsetAsync(dy, 0, sizeof(float) * M * C, st));
+    double* s_dy = stats + (size_t)slot * 2 * 2048;
+    double* s_dyx = s_dy + 2048;
+    const size_t nwin = (size_t)g.B * (H / P) * (W / P);
+    const int wpb = 64;
+    dim3 grid(cdiv(C, 256), (unsigned)((nwin + wpb - 1) / wpb));
+    enc_bwd_route_kernel<GT><<<grid, 256, 0, st>>>(reinterpret_cast<const GT*>(dY), X, mean + slot * 2048, invstd + slot * 2048,
+                                                   gamma, beta, dy, g.B, H, W, C, P, R, wpb, s_dy, s_dyx);
+    DIC_LAUNCH_CHECK();
+    enc_bwd_apply_kernel<bf16><<<enc_grid(M * C), 256, 0, st>>>(dy, X, mean + slot * 2048, invstd + slot * 2048, gamma, s_dy, s_dyx,
+                                                                (double)M, M, C, is_bf16 ? dx16 : nullptr, dgamma, dbeta);
+    DIC_LAUNCH_CHECK();
+    return 0;
+  };
+  // dW = dx^T . rows  (split-K), db = colsum(dx), through the mode's GEMM engine
+  auto wgrad = [&](const float* dx, int C, const ST* rows, int Kp, size_t M, float* dW) -> int {
+    const void* a = is_bf16 ? (const void*)dx16 : (const void*)dx;
+    GemmArgs ga = gemm_args_nt(a, is_bf16, 0, rows, is_bf16, 0, dW, 0, Kp, C, Kp, (int)M, nullptr);
+    ga.a_m = 1; ga.a_k = C; ga.b_n = 1; ga.b_k = Kp;
+    return gemm_splitk(ga, st);
+  };
+
+  // stage 3
+  if (feat_dtype == DIC_BF16)
+    DIC_TRY(stage(bf16{}, d_feats, out3, dy3, 2, g.P2h, g.P2w, g.C3, 1, 2, p.bn3_w, p.bn3_b, gr.bn3_w, gr.bn3_b));
+  else
+    DIC_TRY(stage(float{}, d_feats, out3, dy3, 2, g.P2h, g.P2w, g.C3, 1, 2, p.bn3_w, p.bn3_b, gr.bn3_w, gr.bn3_b));
+  DIC_TRY(launch_colsum(dy3, 0, (int)g.M3(), g.C3, g.C3, gr.conv3_b, st));
+  DIC_TRY(wgrad(dy3, g.C3, p2, g.C2, g.M3(), gr.conv3_w));
+  {
+    const void* a = is_bf16 ? (const void*)dx16 : (const void*)dy3;
+    GemmArgs ga = gemm_args_nt(a, is_bf16, g.C3, w3p, is_bf16, 0, dp2, 0, g.C2, (int)g.M3(), g.C2, g.C3, nullptr);
+    ga.b_n = 1; ga.b_k = g.C2;
+    DIC_TRY(gemm(ga, st));
+  }
+  // stage 2
+  DIC_TRY(stage(float{}, dp2, out2, dy2, 1, g.H2, g.W2, g.C2, 3, 1, p.bn2_w, p.bn2_b, gr.bn2_w, gr.bn2_b));
+  DIC_TRY(launch_colsum(dy2, 0, (int)g.M2(), g.C2, g.C2, gr.conv2_b, st));
+  DIC_TRY(wgrad(dy2, g.C2, col2, K2, g.M2(), dwp));
+  enc_unpack_dw_kernel<<<enc_grid((size_t)g.C2 * K2), 256, 0, st>>>(dwp, gr.conv2_w, g.C2, g.C1, 9, K2);
+  DIC_LAUNCH_CHECK();
+  {
+    const void* a = is_bf16 ? (const void*)dx16 : (const void*)dy2;
+    GemmArgs ga = gemm_args_nt(a, is_bf16, g.C2, w2p, is_bf16, 0, dcol2, 0, K2, (int)g.M2(), K2, g.C2, nullptr);
+    ga.b_n = 1; ga.b_k = K2;
+    DIC_TRY(gemm(ga, st));
+  }
+  enc_col2im3_kernel<<<enc_grid((size_t)g.B * g.P1h * g.P1w * g.C1), 256, 0, st>>>(dcol2, dp1, g.B, g.P1h, g.P1w, g.C1, g.H2, g.W2);
+  DIC_LAUNCH_CHECK();
+  // stage 1
+  DIC_TRY(stage(float{}, dp1, out1, dy1, 0, g.H1, g.W1, g.C1, 3, 1, p.bn1_w, p.bn1_b, gr.bn1_w, gr.bn1_b));
+  DIC_TRY(launch_colsum(dy1, 0, (int)g.M1(), g.C1, g.C1, gr.conv1_b, st));
+  DIC_TRY(wgrad(dy1, g.C1, col1, g.K1p, g.M1(), dwp));
+  enc_unpack_dw_kernel<<<enc_grid((size_t)g.C1 * 49), 256, 0, st>>>(dwp, gr.conv1_w, g.C1, 1, 49, g.K1p);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+
 extern "C" {
 
 int dic_version(void) { return DIC_VERSION; }
@@ -871,6 +1053,41 @@ void dic_set_grads_ready_events(void* ev_linear, void* ev_middle, void* ev_all) 
   g_grads_mid_event.store(reinterpret_cast<cudaEvent_t>(ev_middle));
   g_grads_ready_event.store(reinterpret_cast<cudaEvent_t>(ev_all));
 }
+
+size_t dic_depth_encoder_workspace_bytes(int B, int Hi, int Wi, int dtype) {
+  if (enc_check(B, Hi, Wi, dtype)) return 0;
+  return EncLayout(EncGeom(B, Hi, Wi), dtype).bytes;
+}
+
+int dic_depth_encoder_forward(int dtype, int training, int B, int Hi, int Wi, const float* depth_imgs,
+                              const dic_enc_params* params, float momentum, float eps, void* feats, int feat_dtype,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (enc_check(B, Hi, Wi, dtype)) return -2;
+  if (!depth_imgs || !params || !feats || !workspace) DIC_FAIL(-4, "depth encoder: null pointer");
+  if (feat_dtype != DIC_F32 && feat_dtype != DIC_BF16) DIC_FAIL(-2, "depth encoder: bad feat_dtype");
+  const EncGeom g(B, Hi, Wi);
+  if (workspace_bytes < EncLayout(g, dtype).bytes) DIC_FAIL(-5, "depth encoder: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (dtype == DIC_BF16)
+    return depth_encoder_forward_impl<bf16>(training, g, depth_imgs, *params, momentum, eps, feats, feat_dtype, ws, st);
+  return depth_encoder_forward_impl<float>(training, g, depth_imgs, *params, momentum, eps, feats, feat_dtype, ws, st);
+}
+
+int dic_depth_encoder_backward(int dtype, int B, int Hi, int Wi, const dic_enc_params* params, const void* d_feats,
+                               int feat_dtype, const dic_enc_params* grads, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (enc_check(B, Hi, Wi, dtype)) return -2;
+  if (!params || !d_feats || !grads || !workspace) DIC_FAIL(-4, "depth encoder backward: null pointer");
+  if (feat_dtype != DIC_F32 && feat_dtype != DIC_BF16) DIC_FAIL(-2, "depth encoder: bad feat_dtype");
+  const EncGeom g(B, Hi, Wi);
+  if (workspace_bytes < EncLayout(g, dtype).bytes) DIC_FAIL(-5, "depth encoder: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (dtype == DIC_BF16) return depth_encoder_backward_impl<bf16>(g, *params, d_feats, feat_dtype, *grads, ws, st);
+  return depth_encoder_backward_impl<float>(g, *params, d_feats, feat_dtype, *grads, ws, st);
+}
+
 
 size_t dic_dp_flag_bytes(void) { return kDpFlagWords * sizeof(uint32_t); }
 

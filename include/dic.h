@@ -166,6 +166,29 @@ void dic_set_grads_ready_event(void* event);
  *   ev_all     once all 17 are final (before the dL/dF GEMM, which then leaves some SMs to the all-reduce). */
 void dic_set_grads_ready_events(void* ev_linear, void* ev_middle, void* ev_all);
 
+/* ---- depth CNN encoder -----------------------------------------------------------------------
+ * Replaces Depth_CNN_endoder.forward (depth_models.py:12-56) and its autograd backward: conv 1->128 k7 s3, BN,
+ * ReLU, maxpool 3, conv 128->512 k3, BN, ReLU, maxpool 3, conv 512->2048 k1, BN, ReLU, AdaptiveAvgPool2d(14),
+ * permute -> annotations [B, 196, 2048] written directly in the decoder's layout.  depth_imgs: [B, Hi, Wi] fp32
+ * (one channel; the last feature map must be 7 x 7, i.e. Hi = Wi = 224..232).  All 18 tensors fp32 in the module's
+ * state_dict layout; running_mean / running_var are updated in place when training != 0 (BatchNorm2d semantics:
+ * batch statistics, momentum, unbiased running variance) and used for normalisation otherwise.
+ * feats: out [B, 196, 2048] float32 (feat_dtype = DIC_F32) or bfloat16.  The workspace keeps the activations the
+ * backward needs; dic_depth_encoder_backward takes d_feats [B,196,2048] (dL/dF from dic_decoder_backward) and
+ * writes the 12 parameter gradients (grads: same struct, running_* ignored). */
+typedef struct dic_enc_params {
+  float* conv1_w; float* conv1_b; float* bn1_w; float* bn1_b; float* bn1_mean; float* bn1_var;   /* [128,1,7,7] ... */
+  float* conv2_w; float* conv2_b; float* bn2_w; float* bn2_b; float* bn2_mean; float* bn2_var;   /* [512,128,3,3] ... */
+  float* conv3_w; float* conv3_b; float* bn3_w; float* bn3_b; float* bn3_mean; float* bn3_var;   /* [2048,512,1,1] ... */
+} dic_enc_params;
+size_t dic_depth_encoder_workspace_bytes(int B, int Hi, int Wi, int dtype);
+int dic_depth_encoder_forward(int dtype, int training, int B, int Hi, int Wi, const float* depth_imgs,
+                              const dic_enc_params* params, float momentum, float eps, void* feats, int feat_dtype,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int dic_depth_encoder_backward(int dtype, int B, int Hi, int Wi, const dic_enc_params* params, const void* d_feats,
+                               int feat_dtype, const dic_enc_params* grads, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 /* ---- data-parallel gradient all-reduce over NVLink peer memory ------------------------------
  * The one exchange step of the path.  The reference has no distributed code (config.py:68 pins 'cuda:0'); this
  * replaces the NCCL all-reduce a DistributedDataParallel wrapper would issue after depth_train.py:219 (loss.backward()).

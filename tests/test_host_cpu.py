@@ -79,3 +79,16 @@ def test_hard_attention_noise_matches_reference_draw_order():
     per_step = torch.cat([torch.rand(n, 196) for n in (3, 3, 2, 1)])
     torch.manual_seed(11)
     assert torch.equal(per_step, torch.rand(9, 196))
+
+
+def test_depth_encoder_state_dict_keys_match_reference():
+    """Depth_CNN_endoder keeps the reference's state_dict keys (depth_models.py:12-47, incl. the features.N aliases):
+    checkpoints of depth_train.py:306-322 load unchanged."""
+    import os
+    import numpy as np
+    import depth_image_captioning_pub_b200 as P
+    rec = np.load(os.path.join(os.path.dirname(__file__), "golden", "depth_encoder.npz"))
+    m = P.Depth_CNN_endoder(14)
+    assert sorted(m.state_dict().keys()) == [str(k) for k in rec["keys"]]
+    with __import__("pytest").raises(Exception):
+        m(__import__("torch").zeros(1, 1, 224, 224))          # CPU tensors: no fallback
