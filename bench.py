@@ -524,6 +524,31 @@ def run_b200(args):
         extra["hard_config"] = {"images_per_gpu": B, "max_len": T, "temp": 1.0,
                                 "noise": "torch.rand on the CPU generator per call + H2D (reference semantics)"}
 
+    # ---- depth CNN encoder upstream of the path: forward + backward at the bench batch ----------
+    if not args.no_beam:
+        try:
+            enc = P.Depth_CNN_endoder(14)
+            enc.precision = args.precision
+            enc = enc.to(dev).train()
+            imgs = torch.rand(B, 1, 224, 224, device=dev)
+            dF = torch.randn(B, L, D, device=dev).to(feat_dtype)
+
+            def enc_step():
+                enc(imgs).backward(dF)
+                enc.zero_grad(set_to_none=True)
+            for _ in range(2):
+                enc_step()
+            es = max(3, args.steps // 8)
+            ms_enc = timed(enc_step, es)
+            extra["depth_encoder"] = {"images_per_gpu": B, "ms_fwd_bwd": ms_enc / es,
+                                      "images_per_s": B * world * es / (ms_enc * 1e-3),
+                                      "note": "Depth_CNN_endoder forward + backward (batch statistics), [B,1,224,224] -> "
+                                              "[B,196,2048] annotations in the decoder's dtype; not part of `value`"}
+            del enc, imgs, dF
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001  (an extra: never take the headline line down)
+            extra["depth_encoder"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -536,7 +561,9 @@ def run_b200(args):
             "metric": "train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
-            "data": "synthetic", "config": workload_config(world, B),
+            "data": "synthetic", "config": dict(workload_config(world, B), **({"dp_exchange": allreduce.mode + (
+                " (dic_dp_allreduce: NVLink peer-memory all-reduce kernel" + (", NVLS multimem" if allreduce._peer is not None and allreduce._peer.multicast else "") + ")"
+                if allreduce._peer is not None else "")} if allreduce is not None else {})),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_gpu": e2e_gbs,
                     "h2d_ceiling_gbs_per_gpu": h2d_ceiling_gbs, "frac_of_h2d_ceiling": e2e_gbs / h2d_ceiling_gbs,
