@@ -524,6 +524,31 @@ def run_b200(args):
         extra["hard_config"] = {"images_per_gpu": B, "max_len": T, "temp": 1.0,
                                 "noise": "torch.rand on the CPU generator per call + H2D (reference semantics)"}
 
+    # ---- fp32 parity mode (reference precision; every GEMM on the CUDA-core FMA engine), timed once -----------------
+    if not args.no_beam and args.precision == "bf16":
+        try:
+            m32 = P.CD_RNNDecoderWithSoftAttention(A, E, D, H, V)
+            m32.load_state_dict(m.state_dict())
+            m32.precision = "fp32"
+            m32 = m32.to(dev).train()
+            o32 = P.FusedAdamW(list(m32.parameters()), lr=1e-3)
+            Fr32, Fd32 = F_rgb.float(), F_dep.detach().float().requires_grad_(True)
+
+            def step32():
+                m32.forward_loss(Fr32, Fd32, caps, lengths, ignore_index=V - 1, lam=LAM).backward()
+                o32.step()
+                o32.zero_grad(set_to_none=True)
+                Fd32.grad = None
+            step32()
+            ms32 = timed(step32, 3)
+            extra["fp32_parity_mode"] = {"ms_per_step": ms32 / 3, "tokens_per_s": B * T * world * 3 / (ms32 * 1e-3),
+                                         "note": "same step with fp32 storage and CUDA-core FMA GEMMs (the mode the 1e-4 / "
+                                                 "1e-5 parity bounds are stated for); not the headline"}
+            del m32, o32, Fr32, Fd32
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001
+            extra["fp32_parity_mode"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- depth CNN encoder upstream of the path: forward + backward at the bench batch ----------
     if not args.no_beam:
         try:

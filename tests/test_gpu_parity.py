@@ -198,7 +198,7 @@ def test_forward_backward_vs_oracle(case, precision, cuda_device):
         # bf16 storage of annotations / att1: the spec bounds the logits (2e-2).  alpha and the
         # gradients are reported bounds; the attention-projection gradients see ~0.4% of the ReLU
         # masks flip under bf16 rounding of att1, which the softmax cancellation amplifies.
-        ltol, atol, gtol, gtol_att = LOGIT_TOL_BF16, (2e-2 if peaked else 2e-3), 5e-2, 0.4
+        ltol, atol, gtol, gtol_att = LOGIT_TOL_BF16, (2e-2 if peaked else 2e-3), 5e-2, 0.3     # measured worst case 0.24 (peaked, B = 3); profiles/r02_mask_flip_study.txt
     assert relmax(out.data.detach().cpu(), lo.detach()) <= ltol
     assert np.abs(alphas.detach().cpu().numpy() - ao.detach().numpy()).max() <= atol
     tg = O.pack_targets(caps, lengths).to(cuda_device)
@@ -217,6 +217,8 @@ def test_forward_backward_vs_oracle(case, precision, cuda_device):
             att = k.startswith("attention.encoder_att") or k.startswith("attention.decoder_att")
             tol = (gtol_att if att else gtol) * np.abs(ref).max() + 1e-9
         err = float(np.abs(got - ref).max())
+        if precision == "bf16" and k.startswith("attention."):
+            print(f"[bf16 grad] {case} {k}: max-abs error / max|ref| = {err / (np.abs(ref).max() + 1e-30):.4f}")
         if err > tol:
             bad.append((k, err, tol))
     for name, got, ref in (("d_features", Fr_g.grad, Fr.grad), ("d_depth_features", Fd_g.grad, Fd.grad)):
