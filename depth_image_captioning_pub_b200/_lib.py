@@ -88,6 +88,7 @@ PROTOTYPES = {
     "dic_gemm_nt": (_I, [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
     "dic_gemm_ex": (_I, [_I, _I, _I, _I, _P, _I, C.c_longlong, C.c_longlong, _P, _I, C.c_longlong, C.c_longlong,
                          _P, _P, C.c_longlong, _I, _P]),
+    "dic_gemm_nt_bf16": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, C.c_longlong, _P]),
     "dic_adamw_step": (_I, [_I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                             C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _F, _F, _F, _F, _F, _I, _P]),
     "dic_dfeat_gemm": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -47,10 +47,15 @@ struct HeadArgs {
   int rows;
 };
 
+constexpr int kHeadSlabLd = kHeadDim + 8;                    // bf16 per staged att1 row: 272 bytes, so that the 16-byte
+                                                             // reads of 8 consecutive rows fall into 8 different bank groups
+__host__ __device__ constexpr int head_halves(int KB) { return KB == 1 ? 1 : 2; }   // column halves of the energy pass
 inline size_t attn_head_smem_bytes(int L, int KB) {
   const size_t Lp = (size_t)(L + 3) & ~(size_t)3;
-  return (size_t)head_slabs(KB) * L * kHeadDim * 2 +
-         sizeof(float) * ((size_t)head_cta_rows(KB) * kHeadDim + kHeadDim + (size_t)head_cta_rows(KB) * Lp);
+  return (size_t)head_slabs(KB) * L * kHeadSlabLd * 2 +
+         sizeof(float) * ((size_t)head_cta_rows(KB) * kHeadDim + kHeadDim +
+                          (size_t)head_halves(KB) * head_cta_rows(KB) * Lp) +
+         (size_t)((head_group_rows(KB) + 15) / 16) * 16 * (kHeadDim + 32) * 2;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -78,10 +83,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) attn_head_kernel(const HeadAr
   Trace trace(p.a.trace);
   const int L = p.a.L, D = p.a.D;
   const int Lp = (L + 3) & ~3;
-  bf16* att1_s = reinterpret_cast<bf16*>(smem_raw);                         // [SLABS][L][A]
-  float* att2_s = reinterpret_cast<float*>(att1_s + (size_t)SLABS * L * A);   // [CROWS][A]
+  constexpr int SA = kHeadSlabLd, NH = head_halves(KB);
+  bf16* att1_s = reinterpret_cast<bf16*>(smem_raw);                         // [SLABS][L][SA]
+  float* att2_s = reinterpret_cast<float*>(att1_s + (size_t)SLABS * L * SA);  // [CROWS][A]
   float* w_s = att2_s + CROWS * A;                                          // [A]
-  float* e_s = w_s + A;                                                     // [CROWS][Lp]
+  float* e_s = w_s + A;                                                     // [NH][CROWS][Lp]
+  constexpr int HS = kHeadDim + 32;
+  bf16* h_s = reinterpret_cast<bf16*>(e_s + NH * CROWS * Lp);                // [MT * 16][HS]
 
   const int part = blockIdx.x, grp = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,8 +105,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) attn_head_kernel(const HeadAr
     if (row < p.rows) {
       const int img = row / KB;
       const bf16* src = reinterpret_cast<const bf16*>(p.a.att1) + (size_t)img * L * A;
-      bf16* dst = att1_s + (size_t)r * L * A;
-      for (int i = tid; i < L * A / 8; i += kHeadThreads) cp_async16(dst + i * 8, src + i * 8);
+      bf16* dst = att1_s + (size_t)r * L * SA;
+      for (int i = tid; i < L * A / 8; i += kHeadThreads) cp_async16(dst + (i >> 4) * SA + (i & 15) * 8, src + i * 8);
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -118,24 +126,43 @@ __global__ void __launch_bounds__(kHeadThreads, 1) attn_head_kernel(const HeadAr
     const int col = jj < NT ? A + ncol0 + jj * 8 + 2 * tq : warp * 8 + 2 * tq;
     bz[jj] = *reinterpret_cast<const float2*>(p.bias_db + col);
   }
-  if (tid < A) w_s[tid] = p.a.w_full[tid];
+  // (kept in a register across the wait: a shared-memory store here would make the thread sit out the load's
+  // round trip BEFORE it reaches the dependency wait)
+  const float w_mine = tid < A ? p.a.w_full[tid] : 0.f;
   const float b_full = p.a.b_full[0];
 
   pdl_wait();
   pdl_trigger();
   trace.mark();
+  if (tid < A) w_s[tid] = w_mine;
 
+  // h rows of the group -> shared memory, once per CTA (every warp needs all of them as A fragments; the first
+  // version had each warp fetch them from L2 itself, one dependent round trip per m16 tile: 6.4 us for the three
+  // tiles of a 5-beam group).  Rows are 320 bytes apart: the fragment reads of a quarter-warp (2 rows x 4 chunks)
+  // then fall into 8 different bank groups.
+  {
+    constexpr int CH = MT * 16 * (H / 8);
+#pragma unroll
+    for (int i0 = 0; i0 < CH; i0 += kHeadThreads) {
+      const int i = i0 + tid;
+      if (i < CH) {
+        const int g = i >> 4, ck = i & 15, r = row_base + g;
+        const uint4 v = (g < GROUP && r < p.rows) ? ldg_cg16(p.h + (size_t)r * p.h_ld + ck * 8) : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(h_s + g * HS + ck * 8) = v;
+      }
+    }
+  }
+  __syncthreads();
 #pragma unroll 1
   for (int mt = 0; mt < MT; ++mt) {
-    // ---- h rows of this m16 tile (A fragments) -----------------------------------------------------------
     const int g_lo = mt * 16 + gid, g_hi = g_lo + 8;               // row index inside the group
     const int r_lo = row_base + g_lo, r_hi = row_base + g_hi;
     const bool ok_lo = g_lo < GROUP && r_lo < p.rows, ok_hi = g_hi < GROUP && r_hi < p.rows;
     uint4 ha[4], hb[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      ha[c] = ok_lo ? ldg_cg16(p.h + (size_t)r_lo * p.h_ld + 32 * c + 8 * tq) : make_uint4(0u, 0u, 0u, 0u);
-      hb[c] = ok_hi ? ldg_cg16(p.h + (size_t)r_hi * p.h_ld + 32 * c + 8 * tq) : make_uint4(0u, 0u, 0u, 0u);
+      ha[c] = *reinterpret_cast<const uint4*>(h_s + g_lo * HS + 32 * c + 8 * tq);
+      hb[c] = *reinterpret_cast<const uint4*>(h_s + g_hi * HS + 32 * c + 8 * tq);
     }
     float acc[NT + 1][4];
 #pragma unroll
@@ -180,69 +207,67 @@ __global__ void __launch_bounds__(kHeadThreads, 1) attn_head_kernel(const HeadAr
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  // ---- energies: half-warp per annotation row, 16 bytes (8 columns) per lane -------------------------------
+  // ---- energies: one thread per annotation row (and column half), no cross-lane reduction -------------------
+  // e[j][l] = sum_a w[a] relu(att1[l][a] + att2[j][a]).  A warp owns 32 consecutive annotation rows of one slab
+  // (KB == 1: two slabs, all 128 columns per thread) or of one column half (KB > 1: 64 columns per thread, all KB
+  // rows of the image against one read of the slab); att2 and w come from shared memory as warp-wide broadcasts.
+  // (The first version gave a half-warp to each annotation row: 4 shuffle stages per energy and a re-read of att2
+  // per pass -- 7.5 us of the kernel's 15 us at 5 beams, profiles/r02_beam_phase_times.txt.)
   {
-    const int half = lane >> 4, hl = lane & 15;
-    float w8[8];
+    constexpr int COMBOS = KB == 1 ? SLABS : NH;
+    constexpr int CW = A / NH;                       // columns per thread
+    constexpr int NR = KB == 1 ? 1 : KB;             // att2 rows per thread
+    const int Lw = (L + 31) >> 5;
+    const bool cta_live = arow0 < p.rows;
+    for (int it = warp; it < COMBOS * Lw; it += kHeadThreads / 32) {
+      const int combo = it / Lw, l = (it - combo * Lw) * 32 + lane;
+      const int slab = KB == 1 ? combo : 0, half = KB == 1 ? 0 : combo;
+      if (!cta_live || (KB == 1 && arow0 + slab >= p.rows)) continue;      // warp-uniform
+      const bf16* rowp = att1_s + ((size_t)slab * L + (l < L ? l : L - 1)) * SA + half * CW;
+      const float* a2p = att2_s + (KB == 1 ? slab * A : 0) + half * CW;
+      const float* wp = w_s + half * CW;
+      float sacc[NR];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) w8[q] = w_s[hl * 8 + q];
-    constexpr int RPW = 2 * (kHeadThreads / 32);     // 32 rows per CTA pass
-    if constexpr (KB == 1) {
-#pragma unroll
-      for (int r = 0; r < CROWS; ++r) {
-        if (arow0 + r >= p.rows) continue;             // CTA-uniform
-        float a2[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) a2[q] = att2_s[r * A + hl * 8 + q];
-        const bf16* slab = att1_s + (size_t)r * L * A;
-        for (int lb = 0; lb < L; lb += RPW) {      // warp-uniform trip count: every lane runs the shuffles
-          const int l = lb + warp * 2 + half;
-          float s = 0.f;
-          if (l < L) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(slab + (size_t)l * A + hl * 8);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = __bfloat1622float2(h2[i]);
-              s = fmaf(fmaxf(f.x + a2[2 * i], 0.f), w8[2 * i], s);
-              s = fmaf(fmaxf(f.y + a2[2 * i + 1], 0.f), w8[2 * i + 1], s);
-            }
-          }
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (hl == 0 && l < L) e_s[r * Lp + l] = s + b_full;
-        }
-      }
-    } else if (arow0 < p.rows) {
-      // the KB rows of one image against one read of its att1 slab
-      for (int lb = 0; lb < L; lb += RPW) {
-        const int l = lb + warp * 2 + half;
+      for (int j = 0; j < NR; ++j) sacc[j] = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < CW / 8; ++c) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(rowp + c * 8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = 0.f;
-        if (l < L) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(att1_s + (size_t)l * A + hl * 8);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(h2[i]);
-            v[2 * i] = f.x; v[2 * i + 1] = f.y;
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h2[i]);
+          v[2 * i] = f.x; v[2 * i + 1] = f.y;
         }
+        const float4 w0 = *reinterpret_cast<const float4*>(wp + c * 8), w1 = *reinterpret_cast<const float4*>(wp + c * 8 + 4);
+        const float w8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int j = 0; j < KB; ++j) {
-          float s = 0.f;
+        for (int j = 0; j < NR; ++j) {
+          const float4 a0 = *reinterpret_cast<const float4*>(a2p + j * A + c * 8);
+          const float4 a1 = *reinterpret_cast<const float4*>(a2p + j * A + c * 8 + 4);
+          const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-          for (int q = 0; q < 8; ++q) s = fmaf(fmaxf(v[q] + att2_s[j * A + hl * 8 + q], 0.f), w8[q], s);
+          for (int q = 0; q < 8; ++q) sacc[j] = fmaf(fmaxf(v[q] + a8[q], 0.f), w8[q], sacc[j]);
+        }
+      }
+      if (l < L) {
+        if constexpr (KB == 1) {
+          e_s[slab * Lp + l] = sacc[0] + b_full;
+        } else {
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (hl == 0 && l < L) e_s[j * Lp + l] = s + b_full;
+          for (int j = 0; j < NR; ++j) e_s[(half * CROWS + j) * Lp + l] = sacc[j] + (half == 0 ? b_full : 0.f);
         }
       }
     }
   }
   __syncthreads();
-  if (warp < CROWS && arow0 + warp < p.rows) attn_normalise_row(p.a, e_s + warp * Lp, arow0 + warp, lane);
+  if (warp < CROWS && arow0 + warp < p.rows) {
+    if constexpr (NH == 2) {
+      for (int l = lane; l < L; l += 32) e_s[warp * Lp + l] += e_s[(CROWS + warp) * Lp + l];
+      __syncwarp();
+    }
+    attn_normalise_row(p.a, e_s + warp * Lp, arow0 + warp, lane);
+  }
   trace.end(TK_ALPHA);
 }
 

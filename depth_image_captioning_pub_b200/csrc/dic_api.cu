@@ -1547,4 +1547,16 @@ int dic_gemm_ex(int engine, int M, int N, int K, const void* A, int a_dtype, lon
   return gemm_generic(g, st);
 }
 
+int dic_gemm_nt_bf16(int engine, int M, int N, int K, const void* A, const void* B, const float* bias, void* C,
+                     long long ldc, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || ldc < N) DIC_FAIL(-1, "bad argument");
+  GemmArgs g = gemm_args_nt(A, 1, K, B, 1, K, C, 1, ldc, M, N, K, bias);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (engine == 1) {
+    if (!tc_gemm_eligible(g)) DIC_FAIL(-5, "shape/dtype not eligible for the tcgen05 engine");
+    return tc_gemm(g, st);
+  }
+  return gemm_generic(g, st);
+}
+
 }  // extern "C"

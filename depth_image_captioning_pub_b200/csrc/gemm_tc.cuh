@@ -71,6 +71,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// store of one [rows, 64 bf16] box (128B-swizzled in shared memory) to global memory; rows / columns outside the
+// tensor are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -142,6 +152,7 @@ struct TcArgs {
   int tag;
   int fast_act;
   int b_static;
+  int c_tma;             // bf16 C leaves through shared memory + cp.async.bulk.tensor stores (BN = 128 only)
   int dbg;               // DIC_GEMM_DEBUG=1: CTA 0 prints a globaltimer breakdown of its first tile
   TraceRec* trace;
 };
@@ -154,7 +165,8 @@ constexpr size_t tc_smem_bytes() {
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcArgs p) {
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN");
   static_assert(!B_MN || BN >= 64, "MN-major B needs whole 64-wide blocks");
   extern __shared__ uint8_t smem_raw[];
@@ -347,6 +359,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int e = 0; e < 4; ++e) bzc[c][e] = (pre_bias && n + e < p.N) ? __ldg(p.bias + n + e) : 0.f;
         }
       }
+      // TMA-store path: lane l keeps the bias of columns l and 32 + l of the warp's 64 (broadcast by shuffle later)
+      float bl[2] = {0.f, 0.f};
+      if (BN == 128 && p.c_tma && p.bias != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int n = n0 + grp * COLS + c * 32 + lane;
+          bl[c] = n < p.N ? __ldg(p.bias + n) : 0.f;
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       if (dbg && t == (int)blockIdx.x && warp == 4 && lane == 0) dbg_t[7] = gtimer();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -370,6 +391,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // conflict free), one warp instruction writes 4 full 128-byte row segments.  The epilogue was
       // instruction bound before this (ncu: 15k warp instructions per 64 KB tile), so everything
       // here is 128-bit wide and the bias / activation math is skipped when not requested.
+      if constexpr (BN == 128) {
+        if (p.c_tma) {
+          // bf16 C through shared memory and one bulk tensor store per warp and tile: the warp's [32 rows x 64
+          // columns] block is laid down as 32 rows of 128 bytes in the 128B-swizzle pattern (16-byte chunk k of
+          // row r at chunk k ^ (r & 7): the 8 lanes of a quarter-warp hit 8 different chunks, conflict free) and
+          // leaves as ONE cp.async.bulk.tensor instruction instead of 16 8-byte store instructions per thread,
+          // each of which touched four half-written 128-byte lines (logits GEMM: 48 us for 102 MB before).
+          const uint32_t stg = bar_base + 1024 + (uint32_t)ew * 4096u;
+          if (lane == 0) tma_store_wait_read();        // the previous tile's store has drained this buffer
+          __syncwarp();
+          const bool has_bias = p.bias != nullptr;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                v[e] = __uint_as_float(r[c][k * 8 + e]);
+                if (has_bias) v[e] += __shfl_sync(0xffffffffu, bl[c], k * 8 + e);
+              }
+              uint4 pk;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+              const uint32_t chunk = (uint32_t)((c * 4 + k) ^ (lane & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 128u + chunk * 16u),
+                           "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          const int nb = n0 + grp * COLS, mrow0 = m0 + q * 32;
+          if (lane == 0 && nb < p.N && mrow0 < p.M) {
+            tma_store_2d(&tmC, stg, nb, mrow0);
+            tma_store_commit();
+          }
+          if (dbg && t == (int)blockIdx.x && warp == 4 && lane == 0) dbg_t[9] = gtimer();
+          continue;
+        }
+      }
       if (grp < GROUPS) {
         float* stg = stage_base + ew * (32 * 36);
         const int mrow0 = m0 + q * 32;
@@ -475,6 +537,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (dbg && t == (int)blockIdx.x && warp == 4 && lane == 0) dbg_t[9] = gtimer();
     }
+    if (BN == 128 && p.c_tma && lane == 0) tma_store_wait_all();     // bulk stores complete before the CTA retires
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -537,6 +600,13 @@ inline bool tc_enabled() {
   return v == 1;
 }
 
+// DIC_TMA_STORE=0: bf16 outputs take the per-thread store epilogue (A/B switch of the measurement)
+inline bool tc_tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DIC_TMA_STORE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 inline int tc_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -569,8 +639,8 @@ inline bool tc_gemm_eligible(const GemmArgs& g) {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& p, int grid,
-                          cudaStream_t st) {
+inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& p,
+                          int grid, cudaStream_t st) {
   static DeviceOnce attr_set;
   if (int dev_ = 0; attr_set.need(&dev_)) {
     DIC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -578,7 +648,7 @@ inline int tc_gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     attr_set.mark(dev_);
   }
   DIC_CUDA(launch_pdl(tc_gemm_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kTcThreads), tc_smem_bytes<BN>(), st, tmA, tmB,
-                      p));
+                      tmC, p));
   DIC_LAUNCH_CHECK();
   return 0;
 }
@@ -607,6 +677,14 @@ inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   p.fast_act = g.fast_act;
   p.b_static = g.b_static;
   p.trace = g_trace_host;
+  // bf16 output of a plain (optionally biased) product: bulk tensor stores (see the epilogue)
+  CUtensorMap tmC = tmA;
+  p.c_tma = 0;
+  if (BN == 128 && g.c_bf16 && p.splits == 1 && g.alpha == 1.f && g.sig_hi <= g.sig_lo && g.ldc % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && tc_tma_store_enabled()) {
+    DIC_TRY(make_tmap_bf16(&tmC, g.C, g.M, g.N, g.ldc, 32));
+    p.c_tma = 1;
+  }
   {
     static int dbg_env = -1;
     if (dbg_env < 0) { const char* e = getenv("DIC_GEMM_DEBUG"); dbg_env = (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 0; }
@@ -616,11 +694,11 @@ inline int tc_gemm_bn(const GemmArgs& g, cudaStream_t st) {
   const int grid = (int)(total < tc_num_sms() ? total : tc_num_sms());
   ProfScope prof(g.prof ? g.prof : (int)P_GEMM_TC, st, g.prof_bytes);
   if constexpr (BN >= 64) {
-    if (!a_mn && b_mn) return tc_gemm_launch<BN, false, true>(tmA, tmB, p, grid, st);
-    if (a_mn && b_mn) return tc_gemm_launch<BN, true, true>(tmA, tmB, p, grid, st);
+    if (!a_mn && b_mn) return tc_gemm_launch<BN, false, true>(tmA, tmB, tmC, p, grid, st);
+    if (a_mn && b_mn) return tc_gemm_launch<BN, true, true>(tmA, tmB, tmC, p, grid, st);
   }
-  if (a_mn) return tc_gemm_launch<BN, true, false>(tmA, tmB, p, grid, st);
-  return tc_gemm_launch<BN, false, false>(tmA, tmB, p, grid, st);
+  if (a_mn) return tc_gemm_launch<BN, true, false>(tmA, tmB, tmC, p, grid, st);
+  return tc_gemm_launch<BN, false, false>(tmA, tmB, tmC, p, grid, st);
 }
 
 // Tile width: 128 columns unless that leaves most SMs idle (few tiles, no split-K), then 64 / 32.

@@ -323,6 +323,12 @@ int dic_gemm_ex(int engine, int M, int N, int K, const void* A, int a_dtype, lon
                 long long a_k, const void* B, int b_dtype, long long b_n, long long b_k,
                 const float* bias, float* C, long long ldc, int splits, void* stream);
 
+/* Same product with a bf16 C[M,N] (row stride ldc elements) -- the output mode of the logits / att1 GEMMs of the
+ * bf16 training step (depth_models.py:166,203 in bf16 storage).  engine 1 with ldc % 8 == 0 and a 16-byte aligned C
+ * takes the shared-memory + bulk-tensor-store epilogue (csrc/gemm_tc.cuh). */
+int dic_gemm_nt_bf16(int engine, int M, int N, int K, const void* A, const void* B, const float* bias,
+                     void* C, long long ldc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

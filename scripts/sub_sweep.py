@@ -21,6 +21,8 @@ ap.add_argument("--decode-batch", type=int, default=128)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--subs", default="1,2,3,4,6,8")
 ap.add_argument("--no-decode", action="store_true")
+ap.add_argument("--no-train", action="store_true")
+ap.add_argument("--only-decode-batch", action="store_true")
 ap.add_argument("--tag", default="")
 args = ap.parse_args()
 L, D, A, E, H, V, T = bench.L, bench.D, bench.A, bench.E, bench.H, bench.V, bench.T
@@ -61,7 +63,7 @@ def timed(fn, steps):
 
 
 subs = [int(x) for x in args.subs.split(",")]
-for s in subs:
+for s in ([] if args.no_train else subs):
     lib.dic_set_substreams(s)
     ms = timed(train_step, args.steps)
     print(f"{args.tag}train  B={B} substreams={s}: {ms:.3f} ms/step  {B * T / ms * 1e3:.0f} tokens/s", flush=True)
@@ -72,7 +74,7 @@ if args.no_decode:
 m.eval()
 m.cache_packed_weights = True
 voc = O.synthetic_vocab(V)
-for Bd in sorted({args.decode_batch, 256}):
+for Bd in ([args.decode_batch] if args.only_decode_batch else sorted({args.decode_batch, 256})):
     fr, fd = F_rgb[:Bd].contiguous(), F_dep[:Bd].detach().contiguous()
     for s in subs:
         lib.dic_set_substreams(s)

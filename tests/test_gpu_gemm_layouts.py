@@ -73,3 +73,37 @@ def test_gemm_split_k_atomic(engine, layout, cuda_device):
         out = run(engine, A.t().contiguous().to(dev), 1, M, B.t().contiguous().to(dev), 1, N, M, N, K, None, N, 8, dev)
     err = float((out.double().cpu() - ref).abs().max() / ref.abs().max())
     assert err <= 1e-5, err
+
+
+# bf16 C: the tcgen05 engine's shared-memory + bulk-tensor-store epilogue (ldc % 8 == 0, N tile 128) against the FMA
+# engine and a float64 product.  Shapes cover rows / columns that end inside a 32 x 64 store box, a padded row
+# stride (the canary columns behind N must stay untouched) and the logits shape of the benchmark (5120 x 10000).
+@pytest.mark.parametrize("M,N,K,ldc,with_bias", [
+    (128, 128, 64, 128, True), (200, 136, 128, 136, True), (333, 1000, 192, 1008, False),
+    (5120, 10000, 128, 10000, True), (1568, 128, 2048, 128, True), (130, 264, 64, 272, True)])
+def test_gemm_bf16_out_tma_store(M, N, K, ldc, with_bias, cuda_device):
+    dev = cuda_device
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16).to(dev)
+    bias = torch.randn(N, generator=g).to(dev) if with_bias else None
+    ref = A.double() @ B.double().t()
+    if with_bias:
+        ref = ref + bias.double()
+    outs = []
+    for engine in (1, 0):
+        C = torch.full((M, ldc), 7.0, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.dic_gemm_nt_bf16(engine, M, N, K, A.data_ptr(), B.data_ptr(),
+                                        None if bias is None else bias.data_ptr(), C.data_ptr(), ldc,
+                                        _lib.stream_ptr(dev)))
+        torch.cuda.synchronize()
+        assert bool((C[:, N:] == 7.0).all()), "columns behind N were written"
+        outs.append(C[:, :N].double())
+        # one bf16 rounding of an fp32-accumulated product
+        err = float((outs[-1] - ref).abs().max() / ref.abs().max())
+        assert err <= 2.0 ** -8, (engine, err)
+    # both engines accumulate in fp32 and round once: they may differ by one bf16 ulp where the sums differ in
+    # the last fp32 bits, never by more
+    d = (outs[0] - outs[1]).abs()
+    assert bool((d <= 2.0 ** -7 * (outs[1].abs() + 0.02 * ref.abs().max())).all())
