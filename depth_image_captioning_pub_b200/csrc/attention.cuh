@@ -54,6 +54,10 @@ struct AttnFwdArgs {
   float inv_temp;
   int rpi;              // rows (beams) per image for the alpha kernel's row -> image map (0 = KB)
   int skip_alpha;       // host side: the attention weights were already written by the fused head kernel (attn_head.cuh)
+  int late_wait;        // beam context kernel only: the kernel launched right before this one is NOT a producer of its
+                        // inputs (they come from the launch before that, which the predecessor itself waited for before
+                        // it let this grid start): run concurrently with it, and make the programmatic-dependency wait
+                        // the LAST thing one CTA does, so that this grid's completion still implies the predecessor's
   TraceRec* trace;
 };
 

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_context_mma_cpa_kernel(const 
     if (s < nk) issue(s, s);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  pdl_wait();        // alpha and beta come from the preceding kernels of this step
+  if (!p.late_wait) pdl_wait();        // alpha and beta come from the preceding kernels of this step
   pdl_trigger();
   trace.mark();
   const int row0 = img * KB;
@@ -194,6 +194,10 @@ __global__ void __launch_bounds__(WARPS * 32) attn_context_mma_cpa_kernel(const 
     }
   }
   trace.end(TK_CTX);
+  // late_wait: ONE CTA sits out the predecessor -- enough for "this grid complete => predecessor complete".  (With
+  // every CTA waiting here the first wave kept its slots until the predecessor had finished and the second wave
+  // started 16 us late: profiles/r02_beam_lookahead.txt.)
+  if (p.late_wait && blockIdx.x == 0 && blockIdx.y == 0) pdl_wait();
 }
 
 template <int KB, int WARPS, int STAGES>

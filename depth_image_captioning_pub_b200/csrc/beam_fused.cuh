@@ -218,7 +218,7 @@ struct BeamMergeArgs {
 };
 
 template <typename ST, int K>
-__global__ void __launch_bounds__(256) beam_select_reorder_kernel(const BeamMergeArgs p) {
+__global__ void __launch_bounds__(256, 3) beam_select_reorder_kernel(const BeamMergeArgs p) {      // <= 80 registers: 7 context CTAs fit next to it (decode_impl look-ahead)
   constexpr int SPL = kBfMaxSlicesPerLane;
   constexpr int EPL = (kBfNB + 31) / 32;          // logits of one slice per lane
   constexpr int NC = kBfSel * EPL;                // candidates per lane
@@ -428,9 +428,9 @@ inline bool beam_fused_eligible(int H, int V, int K, int rows) {
   return rows > 0;
 }
 
-template <typename ST, int K>
-inline int launch_beam_fused_k(const void* h_tmp, const void* w_out, const float* b_out, float* logits, float* part,
-                               BeamMergeArgs mg, int rows, int V, cudaStream_t st) {
+// the two launches of a fused beam step; the look-ahead order of decode_impl puts the next step's head kernel between them
+inline int launch_beam_logits_stats(const void* h_tmp, const void* w_out, const float* b_out, float* logits, float* part,
+                                    int rows, int V, cudaStream_t st) {
   const int slices = cdiv(V, kBfNB);
   const int chunks = cdiv(rows, kBfMaxTiles * 128);
   CUtensorMap tmA, tmB;
@@ -444,14 +444,21 @@ inline int launch_beam_fused_k(const void* h_tmp, const void* w_out, const float
   }
   BeamLogitsArgs la;
   la.bias = b_out; la.part = part; la.logits = logits; la.rows = rows; la.V = V; la.slices = slices; la.trace = g_trace_host;
-  {
-    ProfScope prof(P_BEAM_SELECT, st, (double)rows * V * 2);
-    DIC_CUDA(launch_pdl(beam_logits_stats_kernel, dim3(slices, chunks), dim3(kBfThreads),
-                        beam_logits_smem_bytes(kBfMaxTiles), st, tmA, tmB, la));
-    DIC_LAUNCH_CHECK();
+  ProfScope prof(P_BEAM_SELECT, st, (double)rows * V * 2);
+  DIC_CUDA(launch_pdl(beam_logits_stats_kernel, dim3(slices, chunks), dim3(kBfThreads),
+                      beam_logits_smem_bytes(kBfMaxTiles), st, tmA, tmB, la));
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename ST>
+inline int launch_beam_select_reorder(float* logits, float* part, BeamMergeArgs mg, int rows, int V, int K, cudaStream_t st) {
+  mg.part = part; mg.logits = logits; mg.rows = rows; mg.V = V; mg.slices = cdiv(V, kBfNB); mg.trace = g_trace_host;
+  switch (K) {
+    case 3: DIC_CUDA(launch_pdl(beam_select_reorder_kernel<ST, 3>, dim3(rows / K), dim3(256), 0, st, mg)); break;
+    case 5: DIC_CUDA(launch_pdl(beam_select_reorder_kernel<ST, 5>, dim3(rows / K), dim3(256), 0, st, mg)); break;
+    default: DIC_FAIL(-4, "beam_fused: beam %d not instantiated", K);
   }
-  mg.part = part; mg.logits = logits; mg.rows = rows; mg.V = V; mg.slices = slices; mg.trace = g_trace_host;
-  DIC_CUDA(launch_pdl(beam_select_reorder_kernel<ST, K>, dim3(rows / K), dim3(256), 0, st, mg));
   DIC_LAUNCH_CHECK();
   return 0;
 }
@@ -459,11 +466,8 @@ inline int launch_beam_fused_k(const void* h_tmp, const void* w_out, const float
 template <typename ST>
 inline int launch_beam_fused(const void* h_tmp, const void* w_out, const float* b_out, float* logits, float* part,
                              const BeamMergeArgs& mg, int rows, int V, int K, cudaStream_t st) {
-  switch (K) {
-    case 3: return launch_beam_fused_k<ST, 3>(h_tmp, w_out, b_out, logits, part, mg, rows, V, st);
-    case 5: return launch_beam_fused_k<ST, 5>(h_tmp, w_out, b_out, logits, part, mg, rows, V, st);
-    default: DIC_FAIL(-4, "beam_fused: beam %d not instantiated", K);
-  }
+  DIC_TRY(launch_beam_logits_stats(h_tmp, w_out, b_out, logits, part, rows, V, st));
+  return launch_beam_select_reorder<ST>(logits, part, mg, rows, V, K, st);
 }
 
 }  // namespace dic

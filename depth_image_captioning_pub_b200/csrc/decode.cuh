@@ -563,4 +563,24 @@ __global__ void __launch_bounds__(256) beam_state_init_kernel(float* scores, uin
   finished[i] = 0;
 }
 
+// Look-ahead attention of beam search (dic_api.cu decode_impl): the gated contexts were computed for the rows of
+// step t BEFORE the beam selection of that step; row r of step t+1 continues parent back[r] of its image and takes
+// that parent's context.  zg_tmp [rows, D] -> X[r, col_zg : col_zg + D], 16 bytes per thread.
+template <typename ST>
+__global__ void __launch_bounds__(256) beam_gather_ctx_kernel(const ST* __restrict__ zg_tmp, const int32_t* __restrict__ back,
+                                                              ST* __restrict__ X, long long x_row, int col_zg, int rows, int K,
+                                                              int D) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int VEC = 16 / sizeof(ST);
+  const int per_row = D / VEC;
+  const long long n = (long long)rows * per_row;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / per_row), q = (int)(i - (long long)r * per_row);
+    const int src = (r / K) * K + back[r];
+    const uint4 v = *reinterpret_cast<const uint4*>(zg_tmp + (size_t)src * D + (size_t)q * VEC);
+    *reinterpret_cast<uint4*>(X + (size_t)r * x_row + col_zg + (size_t)q * VEC) = v;
+  }
+}
+
 }  // namespace dic

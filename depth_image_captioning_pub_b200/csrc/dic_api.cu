@@ -643,6 +643,12 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
 // =============================================================================================
 // decoding (greedy and beam share the step pipeline; beam = rows_per_image > 1 + selection)
 // =============================================================================================
+// DIC_BEAM_LOOKAHEAD=0: serial order (A/B switch of the measurement and of the parity test)
+static bool lookahead_enabled() {
+  const char* e = getenv("DIC_BEAM_LOOKAHEAD");
+  return !(e && e[0] == '0') && !g_prof.on;      // per-kernel event timing wants kernels timed alone
+}
+
 template <typename ST>
 static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const void* f_rgb,
                        const void* f_depth, int feat_dtype, int B, int K, bool beam, int start_id,
@@ -701,6 +707,23 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
   const int S = sub_bounds(B, pick_substreams(B, 0), 4, i0s);
   cudaStream_t ss[kMaxSub];
   DIC_TRY(sub_fork(st, S, ss));
+  // Look-ahead attention (fused bf16 beam step, one stream of images).  The attention of step t+1 needs h_t of
+  // the row's PARENT only, and the beam selection merely permutes / duplicates the rows of an image: so the
+  // head + context kernels of step t+1 run on the un-reordered h_t, and the children pick up their parent's
+  // gated context by backpointer afterwards (beam_gather_ctx_kernel).  Same kernels on the same per-row inputs as
+  // the serial order: results are bit-identical.  Launch order per step, ONE stream, programmatic launches:
+  //     gates -> lstm -> logits+stats -> head(t+1) -> select+reorder -> context(t+1) -> gather
+  // The context kernel (HBM bound, small CTAs) does not depend on the selection kernel launched right before it
+  // (latency bound, one light CTA per image): it skips its dependency wait and the two run CONCURRENTLY.  Its inputs
+  // come from the head kernel, which is complete by then because the selection kernel lets its dependents start only
+  // after its own wait has returned; the context kernel waits at its very end instead (AttnFwdArgs.late_wait), so the
+  // gather behind it still sees the selection's backpointers.  (A two-stream version with events was measured first:
+  // 5 us per cross-stream hand-over, and the whole-SM logits CTAs starved behind the context grid:
+  // profiles/r02_beam_lookahead.txt.)
+  const bool fused_beam = beam && is_bf16 && !logits_out && !lse_out && beam_fused_eligible(H, V, K, R);
+  const bool lookahead = fused_beam && S == 1 && !alphas_out && !u && attn_head_eligible(A, H, D, L, K) &&
+                         D % 8 == 0 && lookahead_enabled();
+  ST* zg_tmp = reinterpret_cast<ST*>(ws + lay.zg_tmp);
   for (int t = 0; t < max_len; ++t) {
     for (int sb = 0; sb < S; ++sb) {
       const int i0 = i0s[sb], Bs = i0s[sb + 1] - i0;      // images of this sub-batch
@@ -711,28 +734,37 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       ST* Xn = XH + ((size_t)((t + 1) & 1) * R + r0) * XW;
       float* HPs = HP + r0 * (A + D);
       const bool head = is_bf16 && attn_head_eligible(A, H, D, L, K);
-      if (!head) DIC_TRY(hproj<ST>(d, pk, X + E + D, XW, Rs, HPs, sst));
-
-      AttnFwdArgs a;
-      memset(&a, 0, sizeof(a));
-      a.F = F + (size_t)i0 * L * D; a.att1 = att1 + (size_t)i0 * L * A; a.hp = HPs;
-      a.w_full = pk.w_full(); a.b_full = pk.b_full();
-      a.u = u ? u + ((size_t)t * R + r0) * L : nullptr;
-      a.alpha_out = alphas_out ? alphas_out + ((size_t)t * R + r0) * L
-                               : reinterpret_cast<float*>(ws + lay.alpha) + r0 * L;
-      a.alpha_stride = L;
-      a.z_out = nullptr;
-      a.zg_out = X + E; a.zg_stride = XW;
-      a.L = L; a.D = D; a.A = A; a.mode = attn_mode; a.inv_temp = 1.f;
-      if (head) {
-        HeadArgs hd;
-        hd.h = reinterpret_cast<const bf16*>(X + E + D); hd.h_ld = XW;
-        hd.Wdb = reinterpret_cast<const bf16*>(pk.Wdb(d)); hd.bias_db = pk.bias_db();
-        hd.HP = HPs; hd.a = a; hd.rows = Rs;
-        DIC_TRY(launch_attn_head(hd, K, sst));
-        a.skip_alpha = 1;
-      }
-      DIC_TRY(launch_attn_step<ST>(a, Bs, K, sst));
+      // attention of the rows whose hidden state is h (row stride h_ld); gated contexts to zg (row stride zg_ld)
+      // phase 0 = head + context, 1 = head only, 2 = context only (concurrent with its predecessor: late_wait)
+      auto attention = [&](const ST* h, long long h_ld, ST* zg, long long zg_ld, int step, int phase, cudaStream_t s_) -> int {
+        if (!head && phase != 2) DIC_TRY(hproj<ST>(d, pk, h, h_ld, Rs, HPs, s_));
+        AttnFwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.F = F + (size_t)i0 * L * D; a.att1 = att1 + (size_t)i0 * L * A; a.hp = HPs;
+        a.w_full = pk.w_full(); a.b_full = pk.b_full();
+        a.u = u ? u + ((size_t)step * R + r0) * L : nullptr;
+        a.alpha_out = alphas_out ? alphas_out + ((size_t)step * R + r0) * L
+                                 : reinterpret_cast<float*>(ws + lay.alpha) + r0 * L;
+        a.alpha_stride = L;
+        a.z_out = nullptr;
+        a.zg_out = zg; a.zg_stride = zg_ld;
+        a.L = L; a.D = D; a.A = A; a.mode = attn_mode; a.inv_temp = 1.f;
+        if (head) {
+          if (phase != 2) {
+            HeadArgs hd;
+            hd.h = reinterpret_cast<const bf16*>(h); hd.h_ld = h_ld;
+            hd.Wdb = reinterpret_cast<const bf16*>(pk.Wdb(d)); hd.bias_db = pk.bias_db();
+            hd.HP = HPs; hd.a = a; hd.rows = Rs;
+            DIC_TRY(launch_attn_head(hd, K, s_));
+          }
+          a.skip_alpha = 1;
+        }
+        if (phase == 1) return 0;
+        a.late_wait = phase == 2;
+        return launch_attn_step<ST>(a, Bs, K, s_);
+      };
+      // (look-ahead: the contexts of step t > 0 were gathered into X at the end of step t-1)
+      if (!lookahead || t == 0) DIC_TRY(attention(X + E + D, XW, X + E, XW, t, 0, sst));
 
       float* gp = gate_part + r0 * 4 * H;
 
@@ -747,7 +779,7 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       DIC_TRY(lstm_step<ST>(d, pk, X, XW, Rs, R, gp, l, sst));
 
       float* lg = logits_out ? logits_out + ((size_t)t * R + r0) * V : logits_ws + r0 * V;
-      if (beam && is_bf16 && !logits_out && !lse_out && beam_fused_eligible(H, V, K, Rs)) {
+      if (fused_beam) {
         // vocabulary projection + log-sum-exp + per-row top-K in one tcgen05 kernel, merge + reorder in one more
         // (beam_fused.cuh)
         int32_t* back_t = back_ws + (size_t)t * R + r0;
@@ -760,7 +792,16 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
         mg.Xnext = Xn; mg.x_row = XW; mg.col_h = E + D; mg.c = c + r0 * H;
         mg.end_id = end_id; mg.E = E; mg.H = H;
         float* bstats = reinterpret_cast<float*>(ws + lay.bstats) + r0 * 2 * cdiv(V, kBfNB);
-        DIC_TRY(launch_beam_fused<ST>(h_tmp + r0 * H, pk.Wout(), pk.b_out(), lg, bstats, mg, Rs, V, K, sst));
+        const bool more = lookahead && t + 1 < max_len;
+        DIC_TRY(launch_beam_logits_stats(h_tmp + r0 * H, pk.Wout(), pk.b_out(), lg, bstats, Rs, V, sst));
+        if (more) DIC_TRY(attention(h_tmp + r0 * H, H, zg_tmp + r0 * D, D, t + 1, 1, sst));
+        DIC_TRY(launch_beam_select_reorder<ST>(lg, bstats, mg, Rs, V, K, sst));
+        if (more) {
+          DIC_TRY(attention(h_tmp + r0 * H, H, zg_tmp + r0 * D, D, t + 1, 2, sst));
+          DIC_CUDA(launch_pdl(beam_gather_ctx_kernel<ST>, dim3(cdiv(Rs * (D / (16 / (int)sizeof(ST))), 256)), dim3(256), 0,
+                              sst, (const ST*)(zg_tmp + r0 * D), (const int32_t*)back_t, Xn, XW, E, Rs, K, D));
+          DIC_LAUNCH_CHECK();
+        }
         if (step_scores_out)
           DIC_CUDA(cudaMemcpyAsync(step_scores_out + (size_t)t * R + r0, sc[(t + 1) & 1] + r0, sizeof(float) * Rs,
                                    cudaMemcpyDeviceToDevice, sst));

@@ -19,6 +19,7 @@ ap.add_argument("--rows", type=int, default=70)
 ap.add_argument("--beam", type=int, default=5)
 ap.add_argument("--skip", type=int, default=0, help="launches to skip before printing")
 ap.add_argument("--detail", type=int, default=-1, help="kernel id: per-CTA go/exit distribution of one launch")
+ap.add_argument("--concurrent", action="store_true", help="kernels of two streams overlap: split launches per kernel id by repeated block index")
 args = ap.parse_args()
 L, D, A, E, H, V, T = bench.L, bench.D, bench.A, bench.E, bench.H, bench.V, bench.T
 dev = torch.device("cuda", 0)
@@ -69,6 +70,37 @@ names = {1: "alpha", 2: "ctx", 3: "lstm_fwd", 4: "lstm_bwd", 5: "bwd_stream", 6:
 # group into launches: sort by t1 (after-wait), consecutive same kid = one launch
 order = np.argsort(rec["t1"], kind="stable")
 rec = rec[order]
+if args.concurrent:
+    # launches of different streams interleave in time; launches of ONE kernel id do not overlap each other and
+    # every launch holds each block index once: a repeated index starts the next launch
+    rows_ = []
+    for kid in np.unique(rec["kid"]):
+        r = rec[rec["kid"] == kid]
+        seen, start = set(), 0
+        for i in range(len(r) + 1):
+            if i == len(r) or int(r["blk"][i]) in seen:
+                q = r[start:i]
+                rows_.append((int(q["t1"].min()), int(kid), len(q), int(q["t0"].min()), int(q["t2"].max())))
+                if args.detail == int(kid):
+                    dcount = dcount + 1 if "dcount" in globals() else 1
+                    if dcount == 8:
+                        b0 = int(q["t1"].min())
+                        pc = lambda a: " ".join(f"{np.percentile(a, p_):7.2f}" for p_ in (0, 10, 25, 50, 75, 90, 100))
+                        print(f"detail kid={kid}: {len(q)} CTAs; percentiles 0/10/25/50/75/90/100 (us rel. first go)")
+                        print("  entry:", pc((q["t0"].astype(np.int64) - b0) / 1e3))
+                        print("  exit :", pc((q["t2"].astype(np.int64) - b0) / 1e3))
+                        print("  entry->exit per CTA:", pc((q["t2"].astype(np.int64) - q["t0"].astype(np.int64)) / 1e3))
+                seen, start = set(), i
+            if i < len(r):
+                seen.add(int(r["blk"][i]))
+    rows_.sort()
+    T0 = rows_[0][0]
+    print(f"{n} records, {len(rows_)} launches, span {(max(x[4] for x in rows_) - T0) / 1e3:.1f} us")
+    print(f"{'kernel':14s} {'ctas':>5s} {'entry':>9s} {'go':>9s} {'end':>9s} | {'run':>7s}")
+    for k, (t1, kid, nb, t0, t2) in enumerate(rows_):
+        if args.skip <= k < args.skip + args.rows:
+            print(f"{names.get(kid, str(kid)):14s} {nb:5d} {(t0 - T0) / 1e3:9.1f} {(t1 - T0) / 1e3:9.1f} {(t2 - T0) / 1e3:9.1f} | {(t2 - t1) / 1e3:7.1f}")
+    sys.exit(0)
 launches = []
 i = 0
 detail_seen = 0
