@@ -54,7 +54,7 @@ struct AttnFwdArgs {
   float inv_temp;
   int rpi;              // rows (beams) per image for the alpha kernel's row -> image map (0 = KB)
   int skip_alpha;       // host side: the attention weights were already written by the fused head kernel (attn_head.cuh)
-  int late_wait;        // beam context kernel only: the kernel launched right before this one is NOT a producer of its
+  int late_wait;        // decode context kernels: the kernel launched right before this one is NOT a producer of its
                         // inputs (they come from the launch before that, which the predecessor itself waited for before
                         // it let this grid start): run concurrently with it, and make the programmatic-dependency wait
                         // the LAST thing one CTA does, so that this grid's completion still implies the predecessor's
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
       } while (v < p.epoch);
     }
     __syncthreads();
-  } else {
+  } else if (!p.late_wait) {
     pdl_wait();
   }
   pdl_trigger();
@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(kCtxThreads) attn_context_kernel(const AttnFwd
     }
   }
   trace.end(TK_CTX);
+  if (p.late_wait && blockIdx.x == 0 && blockIdx.y == 0) pdl_wait();      // see AttnFwdArgs.late_wait
 }
 
 template <typename ST, int KB>

@@ -723,6 +723,11 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
   const bool fused_beam = beam && is_bf16 && !logits_out && !lse_out && beam_fused_eligible(H, V, K, R);
   const bool lookahead = fused_beam && S == 1 && !alphas_out && !u && attn_head_eligible(A, H, D, L, K) &&
                          D % 8 == 0 && lookahead_enabled();
+  // Greedy decoding, same idea without the reorder: the head kernel of step t+1 follows the logits GEMM of step t, and
+  // the context pass of step t+1 runs next to the arg-max + embedding kernel of step t (both write their own columns
+  // of the next step's input rows):   gates -> lstm -> logits -> head(t+1) -> argmax_embed(t) -> context(t+1)
+  const bool lookahead_g = !beam && is_bf16 && S == 1 && attn_mode == DIC_ATTN_SOFT && !u &&
+                           attn_head_eligible(A, H, D, L, K) && lookahead_enabled();
   ST* zg_tmp = reinterpret_cast<ST*>(ws + lay.zg_tmp);
   for (int t = 0; t < max_len; ++t) {
     for (int sb = 0; sb < S; ++sb) {
@@ -764,7 +769,7 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
         return launch_attn_step<ST>(a, Bs, K, s_);
       };
       // (look-ahead: the contexts of step t > 0 were gathered into X at the end of step t-1)
-      if (!lookahead || t == 0) DIC_TRY(attention(X + E + D, XW, X + E, XW, t, 0, sst));
+      if (!(lookahead || lookahead_g) || t == 0) DIC_TRY(attention(X + E + D, XW, X + E, XW, t, 0, sst));
 
       float* gp = gate_part + r0 * 4 * H;
 
@@ -814,10 +819,13 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
       DIC_TRY(gemm(g, sst));
 
       if (!beam) {
+        const bool more = lookahead_g && t + 1 < max_len;
+        if (more) DIC_TRY(attention(Xn + E + D, XW, Xn + E, XW, t + 1, 1, sst));
         DIC_CUDA(launch_pdl(argmax_embed_kernel<ST>, dim3(Rs), dim3(256), 0, sst, (const float*)lg, V,
                             tokens + r0 * max_len + t, (long long)max_len,
                             reinterpret_cast<const ST*>(pk.Emb()), E, Xn, XW, g_trace_host));
         DIC_LAUNCH_CHECK();
+        if (more) DIC_TRY(attention(Xn + E + D, XW, Xn + E, XW, t + 1, 2, sst));
       } else {
         float* lse_t = lse_out ? lse_out + (size_t)t * R + r0 : lse_ws + r0;
         int32_t* back_t = back_ws + (size_t)t * R + r0;

@@ -81,3 +81,23 @@ def test_lookahead_attention_equals_serial_order(B, K, V, T, cuda_device, monkey
         assert float(ds.max()) <= 1e-5 * max(1.0, float(serial["scores"].abs().max())), float(ds.max())
     n2 = lib.dic_launch_count()
     assert (n2 - n1) == 3 * ((n1 - n0) + (T - 1)), (n1 - n0, n2 - n1)      # one gather per step but the last: it ran
+
+
+@pytest.mark.parametrize("B,V,T", [(128, 10000, 20), (130, 2000, 6), (5, 1000, 9)])
+def test_greedy_lookahead_equals_serial_order(B, V, T, cuda_device, monkeypatch):
+    """Greedy decoding with the same look-ahead order (head of step t+1 after the logits GEMM of step t, context pass
+    next to the arg-max + embedding kernel): tokens as in the serial order."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(1913 + B)
+    F_rgb = torch.rand(B, L, D, generator=g).to(torch.bfloat16).to(dev)
+    F_dep = torch.rand(B, L, D, generator=g).to(torch.bfloat16).to(dev)
+    m = _module(V, dev, seed=99)
+    voc = O.synthetic_vocab(V)
+    monkeypatch.setenv("DIC_BEAM_LOOKAHEAD", "0")
+    serial = m.batch_sample(F_rgb, F_dep, voc, max_length=T)
+    monkeypatch.setenv("DIC_BEAM_LOOKAHEAD", "1")
+    for rep in range(3):
+        look = m.batch_sample(F_rgb, F_dep, voc, max_length=T)
+        torch.cuda.synchronize()
+        same = (look == serial).all(axis=1)          # numpy [B, T]
+        assert float(same.mean()) >= 0.98, float(same.mean())
