@@ -419,6 +419,41 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": dbytes / dcnt if dcnt else None,
                 "avg_launch_us": dms / dcnt * 1e3 if dcnt else None, "launches_per_step": dcnt // args.steps}
 
+    # ---- the same two passes INSIDE the programmatic-launch chain of one real step: the library's in-kernel trace
+    # (thread 0 of every CTA stamps %globaltimer after its dependency wait and at exit; scripts/trace_timeline.py).
+    # The event times above are of each kernel launched alone -- launch latency and the dependency hand-over
+    # included; these are first CTA past its wait -> last CTA out, with the neighbours' prologues overlapped as in
+    # the timed steps.  Reported next to, not instead of, the event-timed fraction.
+    try:
+        import ctypes as C_
+        import numpy as np
+        cap = 2_000_000
+        tbuf = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
+        _lib.check(lib.dic_trace_start(tbuf.data_ptr(), cap))
+        train_step(F_rgb, F_dep, caps)
+        cnt = C_.c_uint(0)
+        _lib.check(lib.dic_trace_stop(C_.byref(cnt)))
+        nrec = min(cnt.value, cap)
+        rec = np.frombuffer(tbuf[: nrec * 32].cpu().numpy().tobytes(),
+                            dtype=np.dtype([("t0", "<u8"), ("t1", "<u8"), ("t2", "<u8"), ("kid", "<i4"), ("blk", "<i4")]))
+        del tbuf
+        in_pipe = {}
+        for name, kid in (("attn_context_fwd", 2), ("attn_stream_bwd", 5)):
+            r = rec[rec["kid"] == kid]
+            r = r[np.argsort(r["t1"], kind="stable")]
+            nl = prof[name][1] // args.steps                                        # launches per step
+            if nl <= 0 or len(r) == 0 or len(r) % nl:
+                continue
+            per = len(r) // nl                                                      # CTAs per launch
+            runs = [(int(q["t2"].max()) - int(q["t1"].min())) / 1e3 for q in np.split(r, len(r) // per)]
+            us = float(np.median(runs))
+            by = prof[name][2] / prof[name][1]
+            in_pipe[name] = {"median_us": us, "achieved_gbs": by / (us * 1e-6) / 1e9, "frac": by / (us * 1e-6) / 1e9 / peak,
+                             "launches": len(runs)}
+        roofline["in_pipeline"] = in_pipe
+    except Exception as e:        # the trace is a diagnostic: never fail the bench line on it
+        roofline["in_pipeline"] = {"error": str(e)[:200]}
+
     # ---- the three big out-of-loop GEMMs against their own roofs (same profiled steps, timed alone by events) ----
     tpeak, tpeak_src = measured_tensor_peak()
     N_rows = B * T

@@ -392,7 +392,9 @@ __global__ void __launch_bounds__(256, 3) beam_select_reorder_kernel(const BeamM
     }
   }
   __syncthreads();
-  // reorder: next-step rows of this image (decode.cuh beam_reorder_kernel)
+  // reorder: next-step rows of this image (decode.cuh beam_reorder_kernel); not in the look-ahead order, where the
+  // next LSTM kernel follows the backpointers itself (Xnext == null)
+  if (p.Xnext == nullptr) { trace.end(TK_BEAM_MERGE); return; }
   const int Wd = p.E + p.H;
   const ST* h_tmp = reinterpret_cast<const ST*>(p.h_tmp);
   const ST* emb = reinterpret_cast<const ST*>(p.emb);
@@ -429,12 +431,12 @@ inline bool beam_fused_eligible(int H, int V, int K, int rows) {
 }
 
 // the two launches of a fused beam step; the look-ahead order of decode_impl puts the next step's head kernel between them
-inline int launch_beam_logits_stats(const void* h_tmp, const void* w_out, const float* b_out, float* logits, float* part,
-                                    int rows, int V, cudaStream_t st) {
+inline int launch_beam_logits_stats(const void* h_tmp, long long h_ld, const void* w_out, const float* b_out, float* logits,
+                                    float* part, int rows, int V, cudaStream_t st) {
   const int slices = cdiv(V, kBfNB);
   const int chunks = cdiv(rows, kBfMaxTiles * 128);
   CUtensorMap tmA, tmB;
-  DIC_TRY(make_tmap_bf16(&tmA, h_tmp, rows, kBfH, kBfH, 128));
+  DIC_TRY(make_tmap_bf16(&tmA, h_tmp, rows, kBfH, h_ld, 128));
   DIC_TRY(make_tmap_bf16(&tmB, w_out, V, kBfH, kBfH, kBfNB));
   static DeviceOnce attr_set;
   if (int dev_ = 0; attr_set.need(&dev_)) {
@@ -466,7 +468,7 @@ inline int launch_beam_select_reorder(float* logits, float* part, BeamMergeArgs 
 template <typename ST>
 inline int launch_beam_fused(const void* h_tmp, const void* w_out, const float* b_out, float* logits, float* part,
                              const BeamMergeArgs& mg, int rows, int V, int K, cudaStream_t st) {
-  DIC_TRY(launch_beam_logits_stats(h_tmp, w_out, b_out, logits, part, rows, V, st));
+  DIC_TRY(launch_beam_logits_stats(h_tmp, kBfH, w_out, b_out, logits, part, rows, V, st));
   return launch_beam_select_reorder<ST>(logits, part, mg, rows, V, K, st);
 }
 

@@ -563,24 +563,74 @@ __global__ void __launch_bounds__(256) beam_state_init_kernel(float* scores, uin
   finished[i] = 0;
 }
 
-// Look-ahead attention of beam search (dic_api.cu decode_impl): the gated contexts were computed for the rows of
-// step t BEFORE the beam selection of that step; row r of step t+1 continues parent back[r] of its image and takes
-// that parent's context.  zg_tmp [rows, D] -> X[r, col_zg : col_zg + D], 16 bytes per thread.
+// LSTM cell of the look-ahead beam step (dic_api.cu decode_impl).  The gate GEMM ran on the rows of step t-1 in
+// PARENT order ([beta.z | h] . [W_z | W_hh]^T, split-K partials); row r of step t continues parent back[r] of its
+// image with token tok[r]:
+//     gates[r] = sum_s part[s][parent] + etab[tok[r]] + (b_ih + b_hh),   c_prev = c_par[parent]
+// so the beam reorder is three index loads here instead of a copy of every row.  h' goes to the h columns of the next
+// parent-order operand, c' to the next parent-order cell buffer.
+struct LstmBeamArgs {
+  const float* gate_part;   // [splits][rows_alloc][4H]
+  long long part_stride;
+  int splits;
+  const float* etab;        // [V, 4H]
+  const float* bias_g;      // [4H]
+  const int32_t* back;      // [rows] parent inside the image
+  const int32_t* tok;       // [rows]
+  const float* c_par;       // [rows, H] parent order
+  float* c_out;             // [rows, H]
+  void* h_out;              // ST, row r at h_out + r*h_stride
+  long long h_stride;
+  int rows, H, K;
+  TraceRec* trace;
+};
+
 template <typename ST>
-__global__ void __launch_bounds__(256) beam_gather_ctx_kernel(const ST* __restrict__ zg_tmp, const int32_t* __restrict__ back,
-                                                              ST* __restrict__ X, long long x_row, int col_zg, int rows, int K,
-                                                              int D) {
+__global__ void __launch_bounds__(256) lstm_beam_kernel(const LstmBeamArgs p) {
+  Trace trace(p.trace);
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const bool live = idx < p.rows * p.H;
+  const int H = p.H;
+  const int r = live ? idx / H : 0, j = live ? idx - r * H : 0;
+  // backpointers, tokens and the parents' cell states are three launches old (selection -> context -> gate GEMM):
+  // complete before this grid may start, loaded before the wait
+  int parent = 0;
+  float c_prev = 0.f, g4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    parent = (r / p.K) * p.K + p.back[r];
+    const int tk = p.tok[r];
+    c_prev = p.c_par[(size_t)parent * H + j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g4[q] = p.bias_g[q * H + j] + p.etab[(size_t)tk * 4 * H + q * H + j];
+  }
   pdl_wait();
   pdl_trigger();
-  constexpr int VEC = 16 / sizeof(ST);
-  const int per_row = D / VEC;
-  const long long n = (long long)rows * per_row;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const int r = (int)(i / per_row), q = (int)(i - (long long)r * per_row);
-    const int src = (r / K) * K + back[r];
-    const uint4 v = *reinterpret_cast<const uint4*>(zg_tmp + (size_t)src * D + (size_t)q * VEC);
-    *reinterpret_cast<uint4*>(X + (size_t)r * x_row + col_zg + (size_t)q * VEC) = v;
+  trace.mark();
+  if (!live) { trace.end(TK_LSTM_FWD); return; }
+  constexpr int kMaxSplits = 16;
+  float part[4][kMaxSplits];
+#pragma unroll
+  for (int sp = 0; sp < kMaxSplits; ++sp) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      part[q][sp] = sp < p.splits ? p.gate_part[(size_t)sp * p.part_stride + (size_t)parent * 4 * H + q * H + j] : 0.f;
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float s = g4[q];
+#pragma unroll
+    for (int sp = 0; sp < kMaxSplits; ++sp) s += part[q][sp];
+    g4[q] = s;
+  }
+  const float ig = sigmoidf_acc(g4[0]);
+  const float fg = sigmoidf_acc(g4[1]);
+  const float gg = tanhf(g4[2]);
+  const float og = sigmoidf_acc(g4[3]);
+  const float c = fg * c_prev + ig * gg;
+  const float h = og * tanhf(c);
+  p.c_out[idx] = c;
+  reinterpret_cast<ST*>(p.h_out)[(size_t)r * p.h_stride + j] = from_f<ST>(h);
+  trace.end(TK_LSTM_FWD);
 }
 
 }  // namespace dic

@@ -179,6 +179,34 @@ static int gates_gemm(const dic_dims& d, const Pack& pk, const ST* X, long long 
   return gemm(g, st);
 }
 
+// the same split-K gate GEMM over an arbitrary operand pair (look-ahead beam step: parent-order rows [beta.z | h]
+// against the columns [E, E+D+H) of the packed [W_ih | W_hh])
+template <typename ST>
+static int gates_gemm_from(const dic_dims& d, const ST* Aop, long long lda, const ST* Bop, long long ldb, int Kdim,
+                           int rows, int rows_alloc, float* gate_part, int* splits_out, cudaStream_t st) {
+  const int is_bf16 = sizeof(ST) == 2;
+  GemmArgs g = gemm_args_nt(Aop, is_bf16, lda, Bop, is_bf16, ldb, gate_part, 0, 4 * d.H, rows, 4 * d.H, Kdim, nullptr);
+  int s;
+  if (tc_gemm_eligible(g)) {
+    const long long tiles = (long long)cdiv(rows, kTcBM) * cdiv(4 * d.H, 64);
+    s = (int)(tc_num_sms() / tiles);
+    const int kb = cdiv(Kdim, kTcBK);
+    if (s > kb / 2) s = kb / 2;
+    g.bn = 64;
+  } else {
+    s = pick_splits(rows, 4 * d.H, Kdim);
+  }
+  if (s > kGateSplitsMax) s = kGateSplitsMax;
+  if (s < 1) s = 1;
+  g.splits = s;
+  g.split_mode = 1;
+  g.split_stride = (long long)rows_alloc * 4 * d.H;
+  g.tag = 2;
+  g.b_static = 1;
+  *splits_out = s;
+  return gemm(g, st);
+}
+
 // one LSTM step: cluster-fused GEMM + pointwise (bf16 mode, gates_lstm.cuh) or split-K GEMM + lstm kernel
 template <typename ST>
 static int lstm_step(const dic_dims& d, const Pack& pk, const ST* X, long long XW, int rows, int rows_alloc,
@@ -708,18 +736,22 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
   cudaStream_t ss[kMaxSub];
   DIC_TRY(sub_fork(st, S, ss));
   // Look-ahead attention (fused bf16 beam step, one stream of images).  The attention of step t+1 needs h_t of
-  // the row's PARENT only, and the beam selection merely permutes / duplicates the rows of an image: so the
-  // head + context kernels of step t+1 run on the un-reordered h_t, and the children pick up their parent's
-  // gated context by backpointer afterwards (beam_gather_ctx_kernel).  Same kernels on the same per-row inputs as
-  // the serial order: results are bit-identical.  Launch order per step, ONE stream, programmatic launches:
-  //     gates -> lstm -> logits+stats -> head(t+1) -> select+reorder -> context(t+1) -> gather
+  // the row's PARENT only, and the beam selection merely permutes / duplicates the rows of an image.  So from the
+  // first selection on nothing is reordered any more: every per-row tensor stays in parent order,
+  //     ZH[t] = [ beta.z of step t+1 | h_t ]   (context kernel | LSTM kernel write their column ranges)
+  // the gate GEMM of step t+1 runs on it as P = ZH[t] . [W_z | W_hh]^T, and the LSTM kernel of step t+1 follows the
+  // backpointers: gates[r] = P[parent(r)] + etab[token(r)] + bias, c_prev = c[parent(r)] (decode.cuh
+  // lstm_beam_kernel; etab = Emb . W_e^T once per call).  Launch order per step, ONE stream, programmatic launches:
+  //     lstm(t) -> logits+stats(t) -> head(t+1) -> select(t) -> context(t+1) -> gate GEMM(t+1) -> lstm(t+1)
   // The context kernel (HBM bound, small CTAs) does not depend on the selection kernel launched right before it
   // (latency bound, one light CTA per image): it skips its dependency wait and the two run CONCURRENTLY.  Its inputs
   // come from the head kernel, which is complete by then because the selection kernel lets its dependents start only
-  // after its own wait has returned; the context kernel waits at its very end instead (AttnFwdArgs.late_wait), so the
-  // gather behind it still sees the selection's backpointers.  (A two-stream version with events was measured first:
-  // 5 us per cross-stream hand-over, and the whole-SM logits CTAs starved behind the context grid:
-  // profiles/r02_beam_lookahead.txt.)
+  // after its own wait has returned; ONE context CTA waits at its very end instead (AttnFwdArgs.late_wait), so the
+  // gate GEMM behind it (and the LSTM kernel behind that) still see the selection's backpointers.  Same arithmetic per
+  // row as the serial order up to the place where the token's share of the gates is added (outside the GEMM here).
+  // (Measured on the way, profiles/r02_beam_lookahead.txt: a two-stream version with events -- 5 us per cross-stream
+  // hand-over, and the whole-SM logits CTAs starved behind the context grid; every context CTA waiting at its end --
+  // the first wave keeps its slots; a gather kernel copying the parents' contexts into child order -- 3.8 us.)
   const bool fused_beam = beam && is_bf16 && !logits_out && !lse_out && beam_fused_eligible(H, V, K, R);
   const bool lookahead = fused_beam && S == 1 && !alphas_out && !u && attn_head_eligible(A, H, D, L, K) &&
                          D % 8 == 0 && lookahead_enabled();
@@ -728,7 +760,14 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
   // of the next step's input rows):   gates -> lstm -> logits -> head(t+1) -> argmax_embed(t) -> context(t+1)
   const bool lookahead_g = !beam && is_bf16 && S == 1 && attn_mode == DIC_ATTN_SOFT && !u &&
                            attn_head_eligible(A, H, D, L, K) && lookahead_enabled();
-  ST* zg_tmp = reinterpret_cast<ST*>(ws + lay.zg_tmp);
+  const long long ZW = (long long)D + H;
+  ST* ZH = reinterpret_cast<ST*>(ws + lay.ZH);               // [2][R][D + H], parent order
+  float* c_par = reinterpret_cast<float*>(ws + lay.c_par);   // [2][R][H]
+  float* etab = reinterpret_cast<float*>(ws + lay.etab);
+  if (lookahead) {
+    GemmArgs g = gemm_args_nt(pk.Emb(), 1, E, pk.Wg(), 1, XW, etab, 0, 4 * H, V, 4 * H, E, nullptr);
+    DIC_TRY(gemm(g, st));
+  }
   for (int t = 0; t < max_len; ++t) {
     for (int sb = 0; sb < S; ++sb) {
       const int i0 = i0s[sb], Bs = i0s[sb + 1] - i0;      // images of this sub-batch
@@ -768,20 +807,41 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
         a.late_wait = phase == 2;
         return launch_attn_step<ST>(a, Bs, K, s_);
       };
-      // (look-ahead: the contexts of step t > 0 were gathered into X at the end of step t-1)
+      // (look-ahead: the contexts of step t > 0 were computed in the previous iteration)
       if (!(lookahead || lookahead_g) || t == 0) DIC_TRY(attention(X + E + D, XW, X + E, XW, t, 0, sst));
 
       float* gp = gate_part + r0 * 4 * H;
-
-      LstmFwdArgs l;
-      memset(&l, 0, sizeof(l));
-      l.bias_g = pk.bias_g();
-      l.c_in = c + r0 * H;
-      l.c_out = beam ? c_tmp + r0 * H : c + r0 * H;
-      l.h_out = beam ? h_tmp + r0 * H : Xn + E + D;
-      l.h_stride = beam ? H : XW;
-      l.rows = Rs; l.H = H;
-      DIC_TRY(lstm_step<ST>(d, pk, X, XW, Rs, R, gp, l, sst));
+      // look-ahead beam: parent-order buffers of this step (h_t, c_t) and the previous one
+      ST* ZHt = ZH + ((size_t)(t & 1) * R + r0) * ZW;
+      float* cpt = c_par + ((size_t)(t & 1) * R + r0) * H;
+      if (lookahead && t > 0) {
+        const ST* ZHp = ZH + ((size_t)((t - 1) & 1) * R + r0) * ZW;
+        int splits = 1;
+        DIC_TRY(gates_gemm_from<ST>(d, ZHp, ZW, reinterpret_cast<const ST*>(pk.Wg()) + E, XW, (int)ZW, Rs, R, gp, &splits, sst));
+        LstmBeamArgs lb;
+        memset(&lb, 0, sizeof(lb));
+        lb.gate_part = gp; lb.part_stride = (long long)R * 4 * H; lb.splits = splits;
+        lb.etab = etab; lb.bias_g = pk.bias_g();
+        lb.back = back_ws + (size_t)(t - 1) * R + r0; lb.tok = tok_ws + (size_t)(t - 1) * R + r0;
+        lb.c_par = c_par + ((size_t)((t - 1) & 1) * R + r0) * H; lb.c_out = cpt;
+        lb.h_out = ZHt + D; lb.h_stride = ZW;
+        lb.rows = Rs; lb.H = H; lb.K = K; lb.trace = g_trace_host;
+        {
+          ProfScope prof(P_LSTM, sst);
+          DIC_CUDA(launch_pdl(lstm_beam_kernel<ST>, dim3(cdiv(Rs * H, 256)), dim3(256), 0, sst, lb));
+          DIC_LAUNCH_CHECK();
+        }
+      } else {
+        LstmFwdArgs l;
+        memset(&l, 0, sizeof(l));
+        l.bias_g = pk.bias_g();
+        l.c_in = c + r0 * H;
+        l.c_out = lookahead ? cpt : (beam ? c_tmp + r0 * H : c + r0 * H);
+        l.h_out = lookahead ? ZHt + D : (beam ? h_tmp + r0 * H : Xn + E + D);
+        l.h_stride = lookahead ? ZW : (beam ? H : XW);
+        l.rows = Rs; l.H = H;
+        DIC_TRY(lstm_step<ST>(d, pk, X, XW, Rs, R, gp, l, sst));
+      }
 
       float* lg = logits_out ? logits_out + ((size_t)t * R + r0) * V : logits_ws + r0 * V;
       if (fused_beam) {
@@ -797,15 +857,15 @@ static int decode_impl(const dic_dims& d, int attn_mode, const void* pack, const
         mg.Xnext = Xn; mg.x_row = XW; mg.col_h = E + D; mg.c = c + r0 * H;
         mg.end_id = end_id; mg.E = E; mg.H = H;
         float* bstats = reinterpret_cast<float*>(ws + lay.bstats) + r0 * 2 * cdiv(V, kBfNB);
-        const bool more = lookahead && t + 1 < max_len;
-        DIC_TRY(launch_beam_logits_stats(h_tmp + r0 * H, pk.Wout(), pk.b_out(), lg, bstats, Rs, V, sst));
-        if (more) DIC_TRY(attention(h_tmp + r0 * H, H, zg_tmp + r0 * D, D, t + 1, 1, sst));
-        DIC_TRY(launch_beam_select_reorder<ST>(lg, bstats, mg, Rs, V, K, sst));
-        if (more) {
-          DIC_TRY(attention(h_tmp + r0 * H, H, zg_tmp + r0 * D, D, t + 1, 2, sst));
-          DIC_CUDA(launch_pdl(beam_gather_ctx_kernel<ST>, dim3(cdiv(Rs * (D / (16 / (int)sizeof(ST))), 256)), dim3(256), 0,
-                              sst, (const ST*)(zg_tmp + r0 * D), (const int32_t*)back_t, Xn, XW, E, Rs, K, D));
-          DIC_LAUNCH_CHECK();
+        if (lookahead) {
+          mg.Xnext = nullptr;                    // nothing is reordered: the next LSTM kernel follows the backpointers
+          const bool more = t + 1 < max_len;
+          DIC_TRY(launch_beam_logits_stats(ZHt + D, ZW, pk.Wout(), pk.b_out(), lg, bstats, Rs, V, sst));
+          if (more) DIC_TRY(attention(ZHt + D, ZW, ZHt, ZW, t + 1, 1, sst));
+          DIC_TRY(launch_beam_select_reorder<ST>(lg, bstats, mg, Rs, V, K, sst));
+          if (more) DIC_TRY(attention(ZHt + D, ZW, ZHt, ZW, t + 1, 2, sst));
+        } else {
+          DIC_TRY(launch_beam_fused<ST>(h_tmp + r0 * H, pk.Wout(), pk.b_out(), lg, bstats, mg, Rs, V, K, sst));
         }
         if (step_scores_out)
           DIC_CUDA(cudaMemcpyAsync(step_scores_out + (size_t)t * R + r0, sc[(t + 1) & 1] + r0, sizeof(float) * Rs,

@@ -137,7 +137,7 @@ struct TrainLayout {
 // Decode workspace: R = B*beam rows.
 struct DecodeLayout {
   size_t Fsum, meanF, att1, XH, HP, c, c_tmp, h_tmp, h0, c0, gate_part, logits, lse;
-  size_t scores, scores2, fin, fin2, back, tok, step_scores, alpha, cand, meanF16, hc0, bstats, zg_tmp;
+  size_t scores, scores2, fin, fin2, back, tok, step_scores, alpha, cand, meanF16, hc0, bstats, ZH, c_par, etab;
   size_t bytes;
   size_t XW;
   int es;
@@ -171,7 +171,10 @@ struct DecodeLayout {
     meanF16 = c_.take((size_t)B * d.D * 2);
     hc0 = c_.take(sizeof(float) * B * 2 * d.H);
     bstats = c_.take(sizeof(float) * 2 * R * ((d.V + 79) / 80));   // per-slice (max, sum-exp) pairs of the fused beam step
-    zg_tmp = c_.take(R * d.D * es);                                  // gated contexts of the un-reordered rows (look-ahead attention)
+    // look-ahead beam step (dic_api.cu decode_impl): rows in PARENT order, double buffered over the steps
+    ZH = c_.take(2 * R * ((size_t)d.D + d.H) * es);                  // [beta.z of step t+1 | h_t]: A operand of the gate GEMM
+    c_par = c_.take(2 * sizeof(float) * R * d.H);                    // c_t
+    etab = c_.take(sizeof(float) * (size_t)d.V * 4 * d.H);           // Emb . W_ih[:, :E]^T: a token's share of the gates
     bytes = c_.off;
   }
 };
