@@ -279,142 +279,6 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
   trace.end(TK_BEAM_TOPK);
 }
 
-// Register-resident variant for V <= 256 x 40 (the 10k vocabulary) with 16-byte aligned rows: a thread keeps its
-// 40 logits (ten 16-byte loads, all in flight at once) in registers from the load to the last selection round --
-// no shared-memory staging, so more rows are resident per SM and a row is one load, one reduction of the
-// (max, sum) pairs and K short rounds.  Same arithmetic and tie-breaking as the kernel above.
-constexpr int kTopkRegChunks = 10;
-template <int K, bool FAST>
-__global__ void __launch_bounds__(256) beam_row_topk_reg_kernel(const float* __restrict__ scores,
-                                                                const uint8_t* __restrict__ finished,
-                                                                const float* __restrict__ logits,
-                                                                const float* __restrict__ lse_in,
-                                                                float* __restrict__ lse_out, int V, int end_id,
-                                                                float* __restrict__ cand_v, int* __restrict__ cand_i,
-                                                                TraceRec* trace_buf) {
-  __shared__ float scratch[64];
-  __shared__ float wv[8];
-  __shared__ int wi[8];
-  __shared__ int s_win;
-  Trace trace(trace_buf);
-  pdl_wait();
-  pdl_trigger();
-  trace.mark();
-  const int r = blockIdx.x;
-  const int j = r % K;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float4* src4 = reinterpret_cast<const float4*>(logits + (size_t)r * V);
-  const int n4 = V / 4;
-  float x[kTopkRegChunks][4];
-#pragma unroll
-  for (int u = 0; u < kTopkRegChunks; ++u) {
-    const int i = tid + u * 256;
-    float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    if (i < n4) t = __ldg(src4 + i);
-    x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][3] = t.w;
-  }
-  float ls;
-  if (lse_in) {
-    ls = lse_in[r];
-  } else {
-    float m = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < kTopkRegChunks; ++u)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) m = fmaxf(m, x[u][q]);
-    float ssum = 0.f;
-    if (m != -INFINITY) {
-#pragma unroll
-      for (int u = 0; u < kTopkRegChunks; ++u)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ssum += exp_sel<FAST>(x[u][q] - m);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, m, o);
-      const float os = __shfl_xor_sync(0xffffffffu, ssum, o);
-      const float nm = fmaxf(m, om);
-      ssum = (nm == -INFINITY) ? 0.f : ssum * exp_sel<FAST>(m - nm) + os * exp_sel<FAST>(om - nm);
-      m = nm;
-    }
-    if (lane == 0) { scratch[warp] = m; scratch[8 + warp] = ssum; }
-    __syncthreads();
-    float gm = scratch[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) gm = fmaxf(gm, scratch[w]);
-    float gs = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) gs += (scratch[w] == -INFINITY) ? 0.f : scratch[8 + w] * exp_sel<FAST>(scratch[w] - gm);
-    ls = gm + logf(gs);
-  }
-  if (tid == 0 && lse_out) lse_out[r] = ls;
-  const float sc = scores[r];
-  const bool fin = finished[r] != 0;
-
-  // candidates in place + the thread's best and runner-up (ascending index order: strict '>' keeps the lowest index)
-  float bv = -INFINITY, b2v = -INFINITY;
-  int bi = 0x7fffffff, b2i = 0x7fffffff;
-#pragma unroll
-  for (int u = 0; u < kTopkRegChunks; ++u) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int v = (tid + u * 256) * 4 + q;
-      float c;
-      if (fin) c = (v == end_id) ? sc : -INFINITY;
-      else c = __fadd_rn(sc, __fsub_rn(x[u][q], ls));
-      x[u][q] = c;
-      if (v < V) {
-        if (bi == 0x7fffffff || c > bv) { b2v = bv; b2i = bi; bv = c; bi = v; }
-        else if (b2i == 0x7fffffff || c > b2v) { b2v = c; b2i = v; }
-      }
-    }
-  }
-  float tv = INFINITY;
-  int ti = -1;
-  auto rescan = [&]() {
-    bv = -INFINITY;
-    bi = 0x7fffffff;
-#pragma unroll
-    for (int u = 0; u < kTopkRegChunks; ++u) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int v = (tid + u * 256) * 4 + q;
-        const float c = x[u][q];
-        const bool elig = v < V && ((c < tv) || (c == tv && v > ti));
-        if (elig && (bi == 0x7fffffff || c > bv)) { bv = c; bi = v; }
-      }
-    }
-  };
-  for (int rd = 0; rd < K; ++rd) {
-    float wvv = bv;
-    int wii = bi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, wvv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, wii, o);
-      if (cand_better(ov, oi, wvv, wii)) { wvv = ov; wii = oi; }
-    }
-    if (lane == 0) { wv[warp] = wvv; wi[warp] = wii; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < 8; ++w)
-        if (cand_better(wv[w], wi[w], wvv, wii)) { wvv = wv[w]; wii = wi[w]; }
-      s_win = wii;
-      cand_v[(size_t)r * K + rd] = wvv;
-      cand_i[(size_t)r * K + rd] = j * V + wii;
-    }
-    __syncthreads();
-    if (bi == s_win && bi != 0x7fffffff) {
-      tv = bv;
-      ti = bi;
-      if (b2i != 0x7fffffff) { bv = b2v; bi = b2i; b2i = 0x7fffffff; }
-      else rescan();
-    }
-    __syncthreads();
-  }
-  trace.end(TK_BEAM_TOPK);
-}
-
 // one warp per image: merge the K sorted row lists (K*K <= 64 candidates, two per lane)
 template <int K>
 __global__ void __launch_bounds__(128) beam_merge_kernel(const float* __restrict__ cand_v,
@@ -470,20 +334,10 @@ inline int launch_beam_select(const float* scores, const uint8_t* finished, cons
   float* cv = reinterpret_cast<float*>(workspace);
   int* ci = reinterpret_cast<int*>(cv + (size_t)B * K * K);
   const int staged = (sizeof(float) * (size_t)V <= 47 * 1024) ? 1 : 0;
-  static int reg_env = -1;
-  if (reg_env < 0) { const char* e = getenv("DIC_TOPK_REG"); reg_env = (e && e[0] == '1') ? 1 : 0; }   // off until measured faster
-  const bool regpath = reg_env == 1 && V % 4 == 0 && V <= 256 * 4 * kTopkRegChunks &&
-                       (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
   ProfScope prof(P_BEAM_SELECT, st, (double)B * K * V * sizeof(float));
 #define DIC_TOPK_CASE(KK)                                                                                  \
   case KK:                                                                                                 \
-    if (regpath && fast)                                                                                   \
-      DIC_CUDA(launch_pdl(beam_row_topk_reg_kernel<KK, true>, dim3(B * KK), dim3(256), 0, st, scores, finished, \
-                          logits, lse_in, lse_out, V, end_id, cv, ci, g_trace_host));                      \
-    else if (regpath)                                                                                      \
-      DIC_CUDA(launch_pdl(beam_row_topk_reg_kernel<KK, false>, dim3(B * KK), dim3(256), 0, st, scores, finished, \
-                          logits, lse_in, lse_out, V, end_id, cv, ci, g_trace_host));                      \
-    else if (fast)                                                                                         \
+    if (fast)                                                                                              \
       DIC_CUDA(launch_pdl(beam_row_topk_kernel<KK, true>, dim3(B * KK), dim3(256), staged ? sizeof(float) * V : 0, \
                           st, scores, finished, logits, lse_in, lse_out, V, end_id, cv, ci, staged, g_trace_host)); \
     else                                                                                                   \

@@ -239,237 +239,10 @@ dfeat_gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   trace.end(TK_MISC);
 }
 
-// ---- v2: A-stationary ----------------------------------------------------------------------------------
-// The kernel above re-loads the A tiles (datt1 | alpha^T of an image) for every one of the D/128 column tiles
-// and the B tiles for both row tiles: 96 KB through TMA per 32 KB of output, and its per-tile time (1.76 us)
-// is exactly that at the ~55 GB/s a single SM gets out of TMA.  Here a work unit is (image, 4 column tiles):
-// the image's A tiles (2 row tiles x 3 K blocks x 16 KB) are loaded ONCE and stay in shared memory, every B
-// tile feeds both row tiles (two accumulators), so 288 KB are loaded per 4 x 2 x 32 KB of output: 2.4x less.
-// Shapes: A <= 128, T <= 64 (3 K blocks) and L <= 256 (2 row tiles); anything else takes the kernel above.
-constexpr int kDf2NG = 4;                 // column tiles per work unit
-constexpr int kDf2BStages = 4;
-struct Dfeat2Args {
-  bf16* dF;
-  const float* dmeanF;
-  float inv_l;
-  int B, L, D, T;
-  int KA, NKB;           // K blocks of segment 1, total K blocks (<= 3)
-  int tpi;               // row tiles per image (1 or 2)
-  int groups;            // ceil(D / (128 * kDf2NG))
-  TraceRec* trace;
-};
-constexpr size_t dfeat2_smem_bytes() {
-  return 1024 + (size_t)2 * 3 * 16384 + (size_t)kDf2BStages * 16384 + 256 + (size_t)kTcEpiWarps * 32 * 36 * sizeof(float);
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1)
-dfeat_gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                   const Dfeat2Args p) {
-  constexpr int BN = 128;
-  constexpr uint32_t TILE = 16384;
-  extern __shared__ uint8_t smem_raw[];
-  Trace trace(p.trace);
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t abuf = base;                                   // [2 row tiles][3 K blocks][16 KB]
-  const uint32_t bring = base + 6 * TILE;                       // [kDf2BStages][16 KB]
-  const uint32_t bar_base = bring + kDf2BStages * TILE;
-  auto bfull = [&](int s) { return bar_base + 8u * s; };
-  auto bempty = [&](int s) { return bar_base + 8u * (kDf2BStages + s); };
-  const uint32_t afull = bar_base + 8u * (2 * kDf2BStages);
-  const uint32_t aempty = afull + 8u;
-  auto tfull = [&](int a) { return afull + 16u + 8u * a; };
-  auto tempty = [&](int a) { return afull + 32u + 8u * a; };
-  const uint32_t tmem_slot = afull + 48u;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* stage_base = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int units = p.B * p.groups;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kDf2BStages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    mbar_init(afull, 1);
-    mbar_init(aempty, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kTcEpiWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_wait();
-  pdl_trigger();
-  trace.mark();
-
-  // unit -> (image, first column tile); groups fastest so the units of an image run close together (A in L2)
-  auto unit_of = [&](int u, int& b, int& nt0, int& ntn) {
-    b = u / p.groups;
-    nt0 = (u - b * p.groups) * kDf2NG;
-    const int nt_total = (p.D + BN - 1) / BN;
-    ntn = min(kDf2NG, nt_total - nt0);
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t bphase = 0, aphase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        int b, nt0, ntn;
-        unit_of(u, b, nt0, ntn);
-        mbar_wait(aempty, aphase ^ 1);
-        mbar_expect_tx(afull, (uint32_t)(p.tpi * p.NKB) * TILE);
-        for (int mt = 0; mt < p.tpi; ++mt) {
-          for (int kb = 0; kb < p.KA; ++kb)
-            tma_load_2d(abuf + (mt * 3 + kb) * TILE, &tmA1, afull, kb * kTcBK, b * p.L + mt * kTcBM);
-          for (int kb = p.KA; kb < p.NKB; ++kb) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              tma_load_2d(abuf + (mt * 3 + kb) * TILE + h * 8192, &tmA2, afull, mt * kTcBM + 64 * h,
-                          b * p.T + (kb - p.KA) * kTcBK);
-          }
-        }
-        aphase ^= 1;
-        for (int nt = 0; nt < ntn; ++nt) {
-          const int n0 = (nt0 + nt) * BN;
-          for (int kb = 0; kb < p.NKB; ++kb) {
-            mbar_wait(bempty(stage), bphase ^ 1);
-            mbar_expect_tx(bfull(stage), TILE);
-            const uint32_t sb = bring + stage * TILE;
-            if (kb < p.KA) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) tma_load_2d(sb + h * 8192, &tmB1, bfull(stage), n0 + 64 * h, kb * kTcBK);
-            } else {
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-                tma_load_2d(sb + h * 8192, &tmB2, bfull(stage), b * p.D + n0 + 64 * h, (kb - p.KA) * kTcBK);
-            }
-            if (++stage == kDf2BStages) { stage = 0; bphase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = umma_idesc_bf16(kTcBM, BN, false, true);
-      constexpr uint32_t idesc2 = umma_idesc_bf16(kTcBM, BN, true, true);
-      constexpr uint32_t k_kmajor = 32 >> 4, k_mnmajor = (16 * 128) >> 4;
-      int stage = 0, acc = 0;
-      uint32_t bphase = 0, aphase = 0, acc_phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        int b, nt0, ntn;
-        unit_of(u, b, nt0, ntn);
-        mbar_wait(afull, aphase);
-        aphase ^= 1;
-        for (int nt = 0; nt < ntn; ++nt) {
-          mbar_wait(tempty(acc), acc_phase ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kb = 0; kb < p.NKB; ++kb) {
-            mbar_wait(bfull(stage), bphase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool seg1 = kb < p.KA;
-            const uint64_t bdesc = umma_desc_mnmajor_sw128(bring + stage * TILE);
-            for (int mt = 0; mt < p.tpi; ++mt) {
-              const uint32_t sa = abuf + (mt * 3 + kb) * TILE;
-              const uint64_t adesc = seg1 ? umma_desc_kmajor_sw128(sa) : umma_desc_mnmajor_sw128(sa);
-              const uint32_t ak = seg1 ? k_kmajor : k_mnmajor;
-              const uint32_t tmem_d = tmem_base + (uint32_t)((acc * 2 + mt) * BN);
-#pragma unroll
-              for (int k = 0; k < kTcBK / 16; ++k)
-                umma_bf16(tmem_d, adesc + ak * k, bdesc + k_mnmajor * k, seg1 ? idesc1 : idesc2, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(bempty(stage));
-            if (++stage == kDf2BStages) { stage = 0; bphase ^= 1; }
-          }
-          umma_commit(tfull(acc));
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-        umma_commit(aempty);          // the A tiles may be replaced once every MMA of this unit has retired
-      }
-    }
-  } else if (warp >= 4) {
-    const int ew = warp - 4;
-    const int q = warp & 3;
-    constexpr int COLS = BN / 2;
-    const int grp = ew >> 2;
-    float* stg = stage_base + ew * (32 * 36);
-    const int rrow = lane >> 3, col4 = (lane & 7) * 4;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      int b, nt0, ntn;
-      unit_of(u, b, nt0, ntn);
-      for (int nt = 0; nt < ntn; ++nt) {
-        const int n0 = (nt0 + nt) * BN;
-        mbar_wait(tfull(acc), acc_phase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int mt = 0; mt < p.tpi; ++mt) {
-          const int lrow0 = mt * kTcBM + q * 32;
-          const int rows_valid = min(32, p.L - lrow0);
-          uint32_t r[COLS / 32][32];
-#pragma unroll
-          for (int c = 0; c < COLS / 32; ++c)
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + mt) * BN + grp * COLS + c * 32), r[c]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < COLS / 32; ++c) {
-            const int nb = n0 + grp * COLS + c * 32;
-            if (nb >= p.D || rows_valid <= 0) continue;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4*>(stg + lane * 36 + j) = make_uint4(r[c][j], r[c][j + 1], r[c][j + 2], r[c][j + 3]);
-            __syncwarp();
-            const int n = nb + col4;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rrow;
-              if (rr < rows_valid && n < p.D) {
-                const float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + col4);
-                const float4 mb = __ldg(reinterpret_cast<const float4*>(p.dmeanF + (size_t)b * p.D + n));
-                uint2 pk;
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-                h2[0] = __floats2bfloat162_rn(fmaf(mb.x, p.inv_l, v.x), fmaf(mb.y, p.inv_l, v.y));
-                h2[1] = __floats2bfloat162_rn(fmaf(mb.z, p.inv_l, v.z), fmaf(mb.w, p.inv_l, v.w));
-                *reinterpret_cast<uint2*>(p.dF + ((size_t)b * p.L + lrow0 + rr) * p.D + n) = pk;
-              }
-            }
-            __syncwarp();
-          }
-        }
-        // both row tiles of this accumulator stage are in registers / stored: hand the TMEM stage back
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-  }
-  trace.end(TK_MISC);
-}
-
-inline bool dfeat2_enabled() {
-  static int v = -1;
-  // off by default: measured 107 us against 100 us for the kernel above at the benchmark shape -- with 2.4x
-  // less operand traffic the time did not move, i.e. the pass is bound by its epilogue (TMEM -> bf16 stores)
-  if (v < 0) { const char* e = getenv("DIC_DFEAT_V2"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
+// (An A-stationary variant -- the image's A tiles resident in shared memory, every B tile feeding both row tiles:
+// 2.4x less operand traffic through TMA -- was built and measured in rounds 1-2: 107 us against 94-100 us for the
+// kernel above at the benchmark shape; removed.  With TMA loads AND the per-thread bf16 stores both near 1.7 us per
+// 128 x 128 tile the pass needs both fixed at once: DESIGN.md section 4, "bf16 GEMM outputs through TMA stores".)
 
 inline bool dfeat_tc_eligible(int A, int D, int Lp) {
   return tc_enabled() && A % 8 == 0 && D % 8 == 0 && Lp % 8 == 0;
@@ -489,26 +262,6 @@ inline int launch_dfeat_tc(const bf16* datt1, const bf16* Wenc, const bf16* alph
   // dz [T][B][D] seen as a row-major [T, B*D] matrix: image b's columns start at b*D, rows t >= T are
   // out of bounds (zero-filled); columns past D belong to the next image and are masked at the store
   DIC_TRY(make_tmap_bf16(&tmB2, dz, T, (long long)B * D, (long long)B * D, kTcBK));
-  if (dfeat2_enabled() && cdiv(A, kTcBK) + cdiv(T, kTcBK) <= 3 && cdiv(T, kTcBK) == 1 && cdiv(L, kTcBM) <= 2) {
-    Dfeat2Args q;
-    q.dF = dF; q.dmeanF = dmeanF; q.inv_l = 1.f / (float)L; q.B = B; q.L = L; q.D = D; q.T = T;
-    q.KA = cdiv(A, kTcBK); q.NKB = q.KA + 1; q.tpi = cdiv(L, kTcBM);
-    q.groups = cdiv(cdiv(D, 128), kDf2NG);
-    q.trace = g_trace_host;
-    const long long units = (long long)B * q.groups;
-    const int grid2 = (int)(units < max_ctas ? units : max_ctas);
-    static DeviceOnce attr2;
-    if (int dev_ = 0; attr2.need(&dev_)) {
-      DIC_CUDA(cudaFuncSetAttribute(dfeat_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)dfeat2_smem_bytes()));
-      attr2.mark(dev_);
-    }
-    ProfScope prof(P_DFEAT, st, (double)B * L * D * 2);
-    DIC_CUDA(launch_pdl(dfeat_gemm2_kernel, dim3(grid2), dim3(kTcThreads), dfeat2_smem_bytes(), st, tmA1, tmB1, tmA2,
-                        tmB2, q));
-    DIC_LAUNCH_CHECK();
-    return 0;
-  }
   DfeatArgs p;
   p.dF = dF; p.dmeanF = dmeanF; p.inv_l = 1.f / (float)L; p.B = B; p.L = L; p.D = D; p.A = A; p.T = T;
   p.tiles_m = B * cdiv(L, kTcBM);
