@@ -188,11 +188,21 @@ static int gates_gemm_from(const dic_dims& d, const ST* Aop, long long lda, cons
   GemmArgs g = gemm_args_nt(Aop, is_bf16, lda, Bop, is_bf16, ldb, gate_part, 0, 4 * d.H, rows, 4 * d.H, Kdim, nullptr);
   int s;
   if (tc_gemm_eligible(g)) {
-    const long long tiles = (long long)cdiv(rows, kTcBM) * cdiv(4 * d.H, 64);
-    s = (int)(tc_num_sms() / tiles);
+    // A CTA's time is what it pulls through TMA (~55 GB/s per SM): (128 + BN) x 64 x 2 bytes per K block, K blocks
+    // = ceil(K / 64 / splits), splits = SMs / tiles.  640 rows: 64-column tiles = 40 tiles x 3 splits x 12 blocks x
+    // 24 KB = 288 KB per CTA, 128-column tiles = 20 tiles x 7 splits x 5 blocks x 32 KB = 160 KB per CTA.
     const int kb = cdiv(Kdim, kTcBK);
-    if (s > kb / 2) s = kb / 2;
-    g.bn = 64;
+    long long best = -1;
+    s = 1;
+    for (int bn = 64; bn <= 128; bn *= 2) {
+      const long long tiles = (long long)cdiv(rows, kTcBM) * cdiv(4 * d.H, bn);
+      int sp = (int)(tc_num_sms() / tiles);
+      if (sp > kb / 2) sp = kb / 2;
+      if (sp > kGateSplitsMax) sp = kGateSplitsMax;
+      if (sp < 1) sp = 1;
+      const long long bytes = (long long)(kTcBM + bn) * kTcBK * 2 * cdiv(kb, sp);
+      if (best < 0 || bytes < best) { best = bytes; s = sp; g.bn = bn; }
+    }
   } else {
     s = pick_splits(rows, 4 * d.H, Kdim);
   }
