@@ -233,6 +233,11 @@ int dic_scale_loss_grads(int dtype, const float* grad_loss, void* d_logits, size
  *   tokens [B,max_len] int64 (best row, <end>-padded), lengths [B] int32, scores [B] fp32;
  *   optional traces: back/toks [max_len,B,beam] int32, step_scores/lse [max_len,B,beam] fp32,
  *   logits_out [max_len,B*beam,V] fp32.
+ *
+ * Kernel order (bf16 mode, the shapes of the reference model; DESIGN.md section 4 "look-ahead attention"): the
+ * attention of step t+1 is computed from h_t before the token / beam selection of step t has finished, the context
+ * pass running next to the selection kernel; beam rows are never physically reordered (the LSTM kernel follows the
+ * backpointers).  Results are those of the serial order (DIC_BEAM_LOOKAHEAD=0) up to fp32 summation order.
  */
 size_t dic_decode_workspace_bytes(const dic_dims* dims, int dtype, int B, int beam);
 
