@@ -54,6 +54,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr));
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct BeamLogitsArgs {
   const float* bias;     // [V]
   float* part;           // [slices][rows] (max, sum-exp) pairs
@@ -144,29 +150,57 @@ beam_logits_stats_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp >= 4) {
     const int ew = warp - 4, q = warp & 3;
     bool staged_ok = false;
+    const bool full_slice = n0 + kBfNB <= p.V;          // CTA-uniform
+    static_assert(kBfNB / 4 == 20, "store pattern below: 5 x 32 lanes = 8 rows of 20 float4");
+    int rb[5], cb[5], so[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      const int idx = b * 32 + lane;
+      rb[b] = idx / 20;
+      cb[b] = idx - rb[b] * 20;
+      so[b] = rb[b] * kBfStageLd + cb[b] * 4;
+    }
     for (int t = ew >> 2; t < tiles; t += 2) {
       mbar_wait(tfull(t), 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float v[kBfNB];
+      {
+        uint32_t vr[kBfNB];          // all five loads in flight, one wait
 #pragma unroll
-      for (int c = 0; c < kBfNB / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * kBfTileCols + c * 16), r);
+        for (int c = 0; c < kBfNB / 16; ++c)
+          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * kBfTileCols + c * 16),
+                             *reinterpret_cast<uint32_t(*)[16]>(&vr[c * 16]));
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[c * 16 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < kBfNB; ++j) v[j] = __uint_as_float(vr[j]);
       }
       const int row = row_base + t * 128 + q * 32 + lane;
+      // This epilogue is instruction-issue bound (ncu: 33 k warp instructions per CTA at 35 % issue activity = the
+      // kernel's 12 us): the common case -- a slice that lies inside the vocabulary, a full 128-row tile -- runs
+      // without per-element masks, reads the bias as float4, and takes exp(x - m) as ONE fused multiply-add into
+      // ex2.approx (__expf costs three multiplies, a compare and the ex2).
       float m = -INFINITY;
+      if (full_slice) {
 #pragma unroll
-      for (int j = 0; j < kBfNB; ++j) {
-        v[j] = (n0 + j < p.V) ? v[j] + bias_s[j] : -INFINITY;
-        m = fmaxf(m, v[j]);
+        for (int j = 0; j < kBfNB; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          m = fmaxf(m, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kBfNB; ++j) {
+          v[j] = (n0 + j < p.V) ? v[j] + bias_s[j] : -INFINITY;
+          m = fmaxf(m, v[j]);
+        }
       }
+      constexpr float kLog2e = 1.4426950408889634f;
+      const float m2 = m * kLog2e;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int j = 0; j < kBfNB; j += 4) {
-        s0 += __expf(v[j] - m); s1 += __expf(v[j + 1] - m); s2 += __expf(v[j + 2] - m); s3 += __expf(v[j + 3] - m);
+        s0 += ex2_ftz(fmaf(v[j], kLog2e, -m2)); s1 += ex2_ftz(fmaf(v[j + 1], kLog2e, -m2));
+        s2 += ex2_ftz(fmaf(v[j + 2], kLog2e, -m2)); s3 += ex2_ftz(fmaf(v[j + 3], kLog2e, -m2));
       }
       if (row < p.rows)
         reinterpret_cast<float2*>(p.part)[(size_t)slice * p.rows + row] = make_float2(m, (s0 + s1) + (s2 + s3));
@@ -180,13 +214,31 @@ beam_logits_stats_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         *reinterpret_cast<float4*>(stg + lane * kBfStageLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
       const int wrow0 = row_base + t * 128 + q * 32;
+      const bool all_in = full_slice && wrow0 + 32 <= p.rows;        // warp-uniform: no bounds checks in the store loop
+      float* gdst = p.logits + (size_t)wrow0 * p.V + n0;
+      // 640 float4 per warp tile, 32 lanes: the (row, chunk) pattern of a lane repeats every 5 instructions with the
+      // row advanced by 8, so the five shared-memory offsets are per-kernel constants and a store is one add away
+      // from the five per-tile pointers (the linear index / 20 of the first version was a third of the loop)
+      if (all_in) {
+        float* g5[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) g5[b] = gdst + (size_t)rb[b] * p.V + cb[b] * 4;
+        const size_t step8 = (size_t)8 * p.V;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 5; ++b)
+            *reinterpret_cast<float4*>(g5[b] + a * step8) =
+                *reinterpret_cast<const float4*>(stg + so[b] + a * (8 * kBfStageLd));
+      } else {
 #pragma unroll 4
-      for (int it = 0; it < kBfNB / 4; ++it) {
-        const int idx = it * 32 + lane;
-        const int rr = idx / (kBfNB / 4), c4 = idx - rr * (kBfNB / 4);
-        const float4 o = *reinterpret_cast<const float4*>(stg + rr * kBfStageLd + c4 * 4);
-        if (wrow0 + rr < p.rows && n0 + c4 * 4 + 3 < p.V)
-          *reinterpret_cast<float4*>(p.logits + (size_t)(wrow0 + rr) * p.V + n0 + c4 * 4) = o;
+        for (int it = 0; it < kBfNB / 4; ++it) {
+          const int idx = it * 32 + lane;
+          const int rr = idx / (kBfNB / 4), c4 = idx - rr * (kBfNB / 4);
+          const float4 o = *reinterpret_cast<const float4*>(stg + rr * kBfStageLd + c4 * 4);
+          if (wrow0 + rr < p.rows && n0 + c4 * 4 + 3 < p.V)
+            *reinterpret_cast<float4*>(gdst + (size_t)rr * p.V + c4 * 4) = o;
+        }
       }
       __syncwarp();
     }
