@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(kCeThreads) loss_ce_row_kernel(const LossArgs 
 // its store: no shared-memory staging, 2 instead of 8 barriers, more rows resident per SM.  The shared-memory
 // kernel above took 80 us for 102 MB in + 102 MB out (its CTAs are latency chains of four barrier-separated
 // passes with 5 resident per SM).
+__device__ __forceinline__ float ce_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr int kCeRegChunks = 5;     // 16-byte chunks per thread: 256 threads x 5 x 8 = 10240 columns
 __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) {
   __shared__ float scratch[64];
@@ -179,43 +184,54 @@ __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) 
   const int tgt = loss_target(p, r);
   const bool valid = tgt != p.ignore_index;
   const int n8 = V / 8;
+  const bool in_range = tgt >= 0 && tgt < V;
+  const bool owner = valid && in_range && (tgt / 8) % 256 == tid;     // the thread whose chunk holds the target column
+  const float x_tgt = owner ? __bfloat162float(lb[tgt]) : 0.f;        // read up front: d_logits is written in place
   uint4 raw[kCeRegChunks];
 #pragma unroll
   for (int u = 0; u < kCeRegChunks; ++u) {
     const int i = tid + u * 256;
     if (i < n8) raw[u] = *reinterpret_cast<const uint4*>(lb + (size_t)i * 8);      // plain loads (in-place d_logits)
   }
+  // The loops below were instruction-issue bound (SASS: ~20 instructions per logit -- a per-element target compare in
+  // two passes, a per-element padding select, __expf = three multiplies + compare + ex2 -- 46 us for a pass whose
+  // HBM floor is 32 us).  Now: the target column is handled by its owner thread outside the loops, padding chunks
+  // are filled once, exp(x - m) is one FMA into ex2.approx.
   float x[kCeRegChunks][8];
   float m = -INFINITY;
 #pragma unroll
   for (int u = 0; u < kCeRegChunks; ++u) {
     const int i = tid + u * 256;
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+    if (i < n8) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 f = __bfloat1622float2(h[q]);
-      x[u][2 * q] = i < n8 ? f.x : -INFINITY;
-      x[u][2 * q + 1] = i < n8 ? f.y : -INFINITY;
-      m = fmaxf(m, fmaxf(x[u][2 * q], x[u][2 * q + 1]));
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        x[u][2 * q] = f.x;
+        x[u][2 * q + 1] = f.y;
+        m = fmaxf(m, fmaxf(f.x, f.y));
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[u][q] = -INFINITY;
     }
   }
   m = block_max(m, scratch);
-  float s = 0.f, x_tgt = 0.f;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float m2 = m * kLog2e;
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int u = 0; u < kCeRegChunks; ++u) {
-    const int v0 = (tid + u * 256) * 8;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (v0 + q == tgt) x_tgt = x[u][q];
-      const float e = __expf(x[u][q] - m);      // exp(-inf) = 0 for the padding lanes
-      x[u][q] = e;
-      s += e;
+    for (int q = 0; q < 8; q += 2) {
+      const float e0 = ce_ex2(fmaf(x[u][q], kLog2e, -m2));          // ex2(-inf) = 0 for the padding lanes
+      const float e1 = ce_ex2(fmaf(x[u][q + 1], kLog2e, -m2));
+      x[u][q] = e0; x[u][q + 1] = e1;
+      s0 += e0; s1 += e1;
     }
   }
-  s = block_sum(s, scratch);
-  // the thread that holds the target column reports the row's nll
-  const bool in_range = tgt >= 0 && tgt < V;
-  const bool owner = valid && in_range && (tgt / 8) % 256 == tid;
+  const float s = block_sum(s0 + s1, scratch);
+  // the thread that holds the target column reports the row's nll and patches that one gradient element
   if (owner) p.nll[r] = m + logf(s) - x_tgt;
   if (tid == 0 && !valid) p.nll[r] = 0.f;
   if (tid == 0 && valid && !in_range) p.nll[r] = nanf("");     // a target outside the vocabulary is a caller bug: make it visible
@@ -227,10 +243,11 @@ __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) 
     if (i < n8) {
       float g[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) g[q] = x[u][q] * ps - ((i * 8 + q == tgt) ? scale : 0.f);
+      for (int q = 0; q < 8; ++q) g[q] = x[u][q] * ps;
       store8<bf16>(out + (size_t)i * 8, g);
     }
   }
+  if (owner) out[tgt] = __float2bfloat16_rn(ce_ex2(fmaf(x_tgt, kLog2e, -m2)) * ps - scale);    // same thread, after its chunk store
 }
 
 // doubly-stochastic regulariser, one CTA per image: S[l] = sum_t alpha[b,t,l];
