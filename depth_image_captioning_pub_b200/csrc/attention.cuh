@@ -63,6 +63,8 @@ struct AttnFwdArgs {
 
 // Normalisation of one row of energies by one warp (in place in shared memory), then the stores of the
 // attention weights: softmax | softmax((e+g)/temp) | one_hot(argmax(e+g))  (attention.py:90, :12-25, :34-48)
+// FAST (bf16 storage, the fused head kernel): exp(v - m) as one FMA into ex2.approx (relative error 2^-22)
+template <bool FAST = false>
 __device__ __forceinline__ void attn_normalise_row(const AttnFwdArgs& p, float* e, int row, int lane) {
   const int L = p.L;
   const float* u = p.u ? p.u + (size_t)row * L : nullptr;
@@ -103,7 +105,7 @@ __device__ __forceinline__ void attn_normalise_row(const AttnFwdArgs& p, float* 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (lane + 32 * i < L) {
-        v[i] = expf(v[i] - m);
+        v[i] = FAST ? ex2_approx(fmaf(v[i], 1.4426950408889634f, -m * 1.4426950408889634f)) : expf(v[i] - m);
         s += v[i];
       }
     }

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) attn_head_kernel(const HeadAr
       for (int l = lane; l < L; l += 32) e_s[warp * Lp + l] += e_s[(CROWS + warp) * Lp + l];
       __syncwarp();
     }
-    attn_normalise_row(p.a, e_s + warp * Lp, arow0 + warp, lane);
+    attn_normalise_row<true>(p.a, e_s + warp * Lp, arow0 + warp, lane);
   }
   trace.end(TK_ALPHA);
 }

@@ -54,12 +54,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr));
 }
 
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 struct BeamLogitsArgs {
   const float* bias;     // [V]
   float* part;           // [slices][rows] (max, sum-exp) pairs
@@ -199,8 +193,8 @@ beam_logits_stats_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int j = 0; j < kBfNB; j += 4) {
-        s0 += ex2_ftz(fmaf(v[j], kLog2e, -m2)); s1 += ex2_ftz(fmaf(v[j + 1], kLog2e, -m2));
-        s2 += ex2_ftz(fmaf(v[j + 2], kLog2e, -m2)); s3 += ex2_ftz(fmaf(v[j + 3], kLog2e, -m2));
+        s0 += ex2_approx(fmaf(v[j], kLog2e, -m2)); s1 += ex2_approx(fmaf(v[j + 1], kLog2e, -m2));
+        s2 += ex2_approx(fmaf(v[j + 2], kLog2e, -m2)); s3 += ex2_approx(fmaf(v[j + 3], kLog2e, -m2));
       }
       if (row < p.rows)
         reinterpret_cast<float2*>(p.part)[(size_t)slice * p.rows + row] = make_float2(m, (s0 + s1) + (s2 + s3));

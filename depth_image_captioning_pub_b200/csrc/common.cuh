@@ -348,7 +348,19 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
 // bf16 mode: ex2.approx + rcp.approx (relative error ~1e-6, far below the bf16 storage of what it gates)
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
+// (four instructions: __expf carries range fix-ups -- three multiplies and a compare around the ex2 -- and __frcp_rn is
+// an IEEE-rounded reciprocal; the gate this feeds is stored / multiplied in bf16)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoidf_fast(float x) { return rcp_approx(1.f + ex2_approx(x * -1.4426950408889634f)); }
 
 // per-step valid batch sizes, passed to kernels by value
 struct StepSizes {

@@ -170,11 +170,6 @@ __global__ void __launch_bounds__(kCeThreads) loss_ce_row_kernel(const LossArgs 
 // its store: no shared-memory staging, 2 instead of 8 barriers, more rows resident per SM.  The shared-memory
 // kernel above took 80 us for 102 MB in + 102 MB out (its CTAs are latency chains of four barrier-separated
 // passes with 5 resident per SM).
-__device__ __forceinline__ float ce_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 constexpr int kCeRegChunks = 5;     // 16-byte chunks per thread: 256 threads x 5 x 8 = 10240 columns
 __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) {
   __shared__ float scratch[64];
@@ -224,8 +219,8 @@ __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) 
   for (int u = 0; u < kCeRegChunks; ++u) {
 #pragma unroll
     for (int q = 0; q < 8; q += 2) {
-      const float e0 = ce_ex2(fmaf(x[u][q], kLog2e, -m2));          // ex2(-inf) = 0 for the padding lanes
-      const float e1 = ce_ex2(fmaf(x[u][q + 1], kLog2e, -m2));
+      const float e0 = ex2_approx(fmaf(x[u][q], kLog2e, -m2));          // ex2(-inf) = 0 for the padding lanes
+      const float e1 = ex2_approx(fmaf(x[u][q + 1], kLog2e, -m2));
       x[u][q] = e0; x[u][q + 1] = e1;
       s0 += e0; s1 += e1;
     }
@@ -247,7 +242,7 @@ __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) 
       store8<bf16>(out + (size_t)i * 8, g);
     }
   }
-  if (owner) out[tgt] = __float2bfloat16_rn(ce_ex2(fmaf(x_tgt, kLog2e, -m2)) * ps - scale);    // same thread, after its chunk store
+  if (owner) out[tgt] = __float2bfloat16_rn(ex2_approx(fmaf(x_tgt, kLog2e, -m2)) * ps - scale);    // same thread, after its chunk store
 }
 
 // doubly-stochastic regulariser, one CTA per image: S[l] = sum_t alpha[b,t,l];
