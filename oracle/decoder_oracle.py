@@ -367,3 +367,66 @@ def beam_search(w: Weights, F_rgb, F_depth, start_id: int, end_id: int, beam: in
                 back=torch.stack(backs), toks=torch.stack(toks),
                 all_scores=torch.stack(all_scores), lse=torch.stack(all_lse),
                 logits=all_logits)
+
+
+def beam_search_lookahead(w: Weights, F_rgb, F_depth, start_id: int, end_id: int, beam: int,
+                          max_length: int):
+    """The SAME search as ``beam_search`` in the order the CUDA path runs it (csrc/dic_api.cu decode_impl,
+    "look-ahead attention"; test infrastructure like the rest of this file).
+
+    The attention of step t+1 needs h_t of a row's PARENT only, and the selection of step t merely permutes /
+    duplicates the rows of an image.  So nothing is reordered: every per-row tensor stays in parent order, the
+    gated context of step t+1 is computed from the un-reordered h_t (before the selection of step t is known), the
+    gate pre-activations are P = [beta*z | h] . [W_z | W_hh]^T on the parents, and a child row r adds its token's
+    share from a table:  gates[r] = P[parent(r)] + (Emb . W_e^T)[token(r)] + b_ih + b_hh,  c_prev = c[parent(r)].
+    tests/test_oracle_golden.py pins this to beam_search (same tokens, backpointers and scores).
+    """
+    feats = _fuse(F_rgb, F_depth)
+    B, L, D = feats.shape
+    K = beam
+    E = w["embed.weight"].shape[1]
+    W_ih, W_hh = w["decode_step.weight_ih"], w["decode_step.weight_hh"]
+    bias_g = w["decode_step.bias_ih"] + w["decode_step.bias_hh"]
+    etab = w["embed.weight"] @ W_ih[:, :E].t()                      # [V, 4H]: a token's share of the gates
+    W_zh = torch.cat((W_ih[:, E:], W_hh), dim=1)                    # [4H, D+H]
+    featsK = feats.unsqueeze(1).expand(B, K, L, D).reshape(B * K, L, D)
+    att1 = feats @ w["attention.encoder_att.weight"].t() + w["attention.encoder_att.bias"]
+    att1 = att1.unsqueeze(1).expand(B, K, L, -1).reshape(B * K, L, -1)
+
+    def gated_context(h):
+        ctx, _ = soft_attention(w, featsK, h, att1)
+        return torch.sigmoid(h @ w["f_beta.weight"].t() + w["f_beta.bias"]) * ctx
+
+    def cell(gates, c_prev):
+        i, f, gg, o = gates.chunk(4, dim=1)
+        c2 = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(gg)
+        return torch.sigmoid(o) * torch.tanh(c2), c2
+
+    h0, c0 = init_state(w, feats)
+    h = h0.unsqueeze(1).expand(B, K, -1).reshape(B * K, -1)         # parent order from here on
+    c = c0.unsqueeze(1).expand(B, K, -1).reshape(B * K, -1)
+    parent = torch.arange(B * K)                                     # step 0: every row is its own parent
+    tok_prev = torch.full((B * K,), start_id, dtype=torch.int64)
+    zg = gated_context(h)                                            # context of step 0 (in order)
+    scores = feats.new_full((B, K), float("-inf"))
+    scores[:, 0] = 0.0
+    finished = torch.zeros(B, K, dtype=torch.bool)
+    backs, toks = [], []
+    for t in range(max_length):
+        P = torch.cat((zg, h), dim=1) @ W_zh.t()                     # gate GEMM on the parents
+        h, c = cell(P[parent] + etab[tok_prev] + bias_g, c[parent])  # the LSTM kernel follows the backpointers
+        logits = (h @ w["linear.weight"].t() + w["linear.bias"]).reshape(B, K, -1)
+        if t + 1 < max_length:
+            zg = gated_context(h)                                    # look-ahead: before the selection below
+        lse = torch.logsumexp(logits, dim=2)
+        scores, back, tok, finished = beam_select(scores, finished, logits, lse, end_id)
+        parent = (back + torch.arange(B).unsqueeze(1) * K).reshape(-1)
+        tok_prev = tok.reshape(-1)
+        backs.append(back.to(torch.int32)); toks.append(tok)
+    T = max_length
+    out = torch.full((B, T), end_id, dtype=torch.int64)
+    row = torch.zeros(B, dtype=torch.int64)
+    for t in range(T - 1, -1, -1):
+        out[:, t] = toks[t][torch.arange(B), row]
+        row = backs[t][torch.arange(B), row].to(torch.int64)
+    return dict(tokens=out, scores=scores[:, 0].clone(), back=torch.stack(backs), toks=torch.stack(toks))

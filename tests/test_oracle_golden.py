@@ -111,3 +111,21 @@ def test_beam_spec_properties():
     assert int(b5["back"].min()) >= 0 and int(b5["back"].max()) < 5
     s = b5["all_scores"][:, :, 0]
     assert (s[1:] <= s[:-1] + 1e-6).all()
+
+
+def test_lookahead_beam_order_is_the_same_search():
+    """The kernel order of the CUDA beam path (attention of step t+1 from the un-reordered h_t, gate GEMM in parent
+    order, LSTM following the backpointers, the token's share of the gates from a table) restated in the oracle:
+    in float64 it must pick the same tokens / backpointers and reach the same scores as the serial specification."""
+    A, E, D, H, V, L, B, K, T = 16, 12, 24, 20, 60, 9, 5, 3, 7
+    w = {k: v.double() for k, v in O.make_weights(A, E, D, H, V, seed=5).items()}
+    g = torch.Generator().manual_seed(6)
+    F_rgb = torch.rand(B, L, D, generator=g, dtype=torch.float64)
+    F_dep = torch.rand(B, L, D, generator=g, dtype=torch.float64)
+    voc = O.synthetic_vocab(V)
+    ref = O.beam_search(w, F_rgb, F_dep, voc["<start>"], voc["<end>"], K, T)
+    look = O.beam_search_lookahead(w, F_rgb, F_dep, voc["<start>"], voc["<end>"], K, T)
+    assert torch.equal(look["tokens"], ref["tokens"])
+    assert torch.equal(look["back"], ref["back"])
+    assert torch.equal(look["toks"], ref["toks"])
+    assert float((look["scores"] - ref["scores"]).abs().max()) <= 1e-10
