@@ -101,8 +101,13 @@ class _DecoderBase(nn.Module):
         H = self._dims[3]
         if p >= 1.0:
             return torch.zeros(total, H, device=device)
-        keep = torch.rand(total, H, device=device) >= p     # nn.Dropout on h (depth_models.py:197)
-        return keep.to(torch.float32) / (1.0 - p)
+        # nn.Dropout on h (depth_models.py:197): the keep / (1 - p) mask of the device generator, drawn by ONE kernel
+        # (torch's fused dropout on a cached tensor of ones) instead of rand, compare, cast and divide
+        ones = getattr(self, "_ones_cache", None)
+        if ones is None or ones.shape != (total, H) or ones.device != device:
+            ones = torch.ones(total, H, device=device)
+            self._ones_cache = ones
+        return torch.nn.functional.dropout(ones, p, training=True)
 
     def _teacher_forced(self, attn_mode, features, depth_features, captions, lengths, u, temp, train_dropout):
         features, depth_features = self._check_feats(features, depth_features)
