@@ -66,9 +66,50 @@ static int gemm(const GemmArgs& g, cudaStream_t st) {
   return gemm_generic(g, st);
 }
 
+// Several buffers cleared by ONE launch.  The backward used to enqueue a cudaMemsetAsync in front of each of its
+// twelve split-K / accumulation targets and four device-to-device copies for the bias slices: every such node is
+// its own small grid with a full (non-programmatic) dependency on both sides, ~3 us of stream time each.
+constexpr int kZeroJobsMax = 12;
+struct ZeroJobs {
+  void* p[kZeroJobsMax];
+  unsigned long long bytes[kZeroJobsMax];
+  int n = 0;
+  void add(void* ptr, size_t b) {
+    if (ptr && b && n < kZeroJobsMax) { p[n] = ptr; bytes[n] = b; ++n; }
+  }
+};
+__global__ void __launch_bounds__(256) zero_many_kernel(const ZeroJobs j) {
+  const int job = blockIdx.y;
+  char* base = reinterpret_cast<char*>(j.p[job]);
+  const unsigned long long nb = j.bytes[job];
+  const unsigned long long i0 = (unsigned long long)blockIdx.x * 256 + threadIdx.x, stride = (unsigned long long)gridDim.x * 256;
+  if (((reinterpret_cast<uintptr_t>(base) | nb) & 15) == 0) {
+    uint4* q = reinterpret_cast<uint4*>(base);
+    for (unsigned long long i = i0; i < nb / 16; i += stride) q[i] = make_uint4(0u, 0u, 0u, 0u);
+  } else {                                     // fp32 buffers: always 4-byte aligned
+    float* q = reinterpret_cast<float*>(base);
+    for (unsigned long long i = i0; i < nb / 4; i += stride) q[i] = 0.f;
+  }
+}
+static int launch_zero_many(const ZeroJobs& j, cudaStream_t st) {
+  if (j.n == 0) return 0;
+  zero_many_kernel<<<dim3(64, j.n), 256, 0, st>>>(j);
+  DIC_LAUNCH_CHECK();
+  return 0;
+}
+// column sums of G -> the four bias gradients they belong to (b_ih and b_hh share the gate slice)
+__global__ void __launch_bounds__(256) bias_scatter_kernel(const float* __restrict__ gsum, float* b_ih, float* b_hh, float* dec_att_b,
+                                                           float* fbeta_b, int H4, int A, int D) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < H4) { const float v = gsum[i]; b_ih[i] = v; b_hh[i] = v; }
+  else if (i < H4 + A) dec_att_b[i - H4] = gsum[i];
+  else if (i < H4 + A + D) fbeta_b[i - H4 - A] = gsum[i];
+}
+
 // Dense fp32 output with a long contraction and few output tiles (weight gradients, dHout):
-// split K so the grid covers the SMs about twice; C is zero-filled and accumulated atomically.
-static int gemm_splitk(GemmArgs g, cudaStream_t st) {
+// split K so the grid covers the SMs about twice; C is zero-filled (here, or by the caller: `zeroed`) and
+// accumulated atomically.
+static int gemm_splitk(GemmArgs g, cudaStream_t st, bool zeroed = false) {
   int s = 1;
   if (g.ldc == g.N && !g.c_bf16 && !g.accumulate && g.batch == 1) {
     if (tc_gemm_eligible(g)) {
@@ -83,7 +124,7 @@ static int gemm_splitk(GemmArgs g, cudaStream_t st) {
   }
   g.splits = s;
   g.split_mode = 0;
-  if (s > 1) DIC_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.ldc, st));
+  if (s > 1 && !zeroed) DIC_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.ldc, st));
   return gemm(g, st);
 }
 
@@ -442,8 +483,22 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     DIC_CUDA(cudaMemsetAsync(dwfull_part, 0, sizeof(float) * TB * A, st));
     DIC_CUDA(cudaMemsetAsync(dbfull_part, 0, sizeof(float) * TB, st));
   }
-  DIC_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * B * H, st));
-  DIC_CUDA(cudaMemsetAsync(dc, 0, sizeof(float) * B * H, st));
+  {
+    // everything this backward accumulates into, cleared by one launch (see ZeroJobs)
+    ZeroJobs z;
+    z.add(dh, sizeof(float) * B * H);
+    z.add(dc, sizeof(float) * B * H);
+    z.add(dHout, sizeof(float) * (size_t)total * H);
+    z.add(gr.lin_w, sizeof(float) * (size_t)V * H);
+    z.add(gr.init_w, sizeof(float) * (size_t)2 * H * D);
+    z.add(gr.w_ih, sizeof(float) * (size_t)4 * H * (E + D));
+    z.add(gr.w_hh, sizeof(float) * (size_t)4 * H * H);
+    z.add(gr.dec_att_w, sizeof(float) * (size_t)A * H);
+    z.add(gr.fbeta_w, sizeof(float) * (size_t)D * H);
+    z.add(gr.enc_att_w, sizeof(float) * (size_t)A * D);
+    z.add(gr.embed_w, sizeof(float) * (size_t)V * E);
+    DIC_TRY(launch_zero_many(z, st));
+  }
 
   // bf16 mode: the two contractions over d_logits take a bf16 copy (tensor-core operand)
   const void* dl = d_logits;
@@ -461,7 +516,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   {
     GemmArgs g = gemm_args_nt(dl, dl_bf16, V, pk.Wout(), is_bf16, 0, dHout, 0, H, total, H, V, nullptr);
     g.b_n = 1; g.b_k = H;
-    DIC_TRY(gemm_splitk(g, st));
+    DIC_TRY(gemm_splitk(g, st, true));
   }
 
   // linear (vocabulary projection): its gradients need d_logits and the saved dropout(h) only, so they are
@@ -469,7 +524,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   {
     GemmArgs g = gemm_args_nt(dl, dl_bf16, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
     g.a_m = 1; g.a_k = V; g.b_n = 1; g.b_k = H;
-    DIC_TRY(gemm_splitk(g, st));
+    DIC_TRY(gemm_splitk(g, st, true));
     DIC_TRY(launch_colsum(dl, dl_bf16, total, V, V, gr.lin_b, st));   // bf16 mode: half the bytes
     if (cudaEvent_t ev = g_grads_lin_event.exchange(nullptr)) DIC_CUDA(cudaEventRecord(ev, st));
   }
@@ -582,7 +637,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     {
       GemmArgs g = gemm_args_nt(dhc16, 1, 0, mean16, 1, 0, gr.init_w, 0, D, 2 * H, D, B, nullptr);
       g.a_m = 1; g.a_k = 2 * H; g.b_n = 1; g.b_k = D;
-      DIC_TRY(gemm_splitk(g, st));
+      DIC_TRY(gemm_splitk(g, st, true));
     }
     if (d_feats) {
       GemmArgs m = gemm_args_nt(dhc16, 1, 2 * H, pk.Winit(), 1, 0, dmeanF, 0, D, B, D, 2 * H, nullptr);
@@ -610,17 +665,15 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   {
     float* gsum = reinterpret_cast<float*>(ws + lay.tmpvec);
     DIC_TRY(launch_colsum(G, is_bf16, (int)TB, (int)GW, GW, gsum, st));
-    DIC_CUDA(cudaMemcpyAsync(gr.b_ih, gsum, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
-    DIC_CUDA(cudaMemcpyAsync(gr.b_hh, gsum, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
-    DIC_CUDA(cudaMemcpyAsync(gr.dec_att_b, gsum + 4 * H, sizeof(float) * A, cudaMemcpyDeviceToDevice, st));
-    DIC_CUDA(cudaMemcpyAsync(gr.fbeta_b, gsum + 4 * H + A, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+    bias_scatter_kernel<<<cdiv(4 * H + A + D, 256), 256, 0, st>>>(gsum, gr.b_ih, gr.b_hh, gr.dec_att_b, gr.fbeta_b, 4 * H, A, D);
+    DIC_LAUNCH_CHECK();
   }
 
   auto wgrad = [&](const ST* Aop, long long a_ld, int M, const ST* Bop, long long b_ld, int N, int K,
                    float* C, long long ldc) -> int {
     GemmArgs g = gemm_args_nt(Aop, is_bf16, 0, Bop, is_bf16, 0, C, 0, ldc, M, N, K, nullptr);
     g.a_m = 1; g.a_k = a_ld; g.b_n = 1; g.b_k = b_ld;
-    return gemm_splitk(g, st);
+    return gemm_splitk(g, st, true);
   };
   // [dW_ih | dW_hh] = dgates^T . [emb|zg|h]
   DIC_TRY(wgrad(G, GW, 4 * H, XH, XW, E + D, (int)TB, gr.w_ih, E + D));
@@ -634,7 +687,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     GemmArgs g = gemm_args_nt(G, is_bf16, GW, pk.Wg(), is_bf16, 0, dXemb, 0, E, (int)TB, E, 4 * H, nullptr);
     g.b_n = 1; g.b_k = XW;
     DIC_TRY(gemm(g, st));
-    DIC_CUDA(cudaMemsetAsync(gr.embed_w, 0, sizeof(float) * (size_t)V * E, st));
+    // (gr.embed_w was cleared with the other accumulation targets at the top)
     dim3 grid(cdiv(B * E, 256), T);
     embed_scatter_add_kernel<<<grid, 256, 0, st>>>(dXemb, captions, cap_stride, gr.embed_w, B, E, V, sizes, T);
     DIC_LAUNCH_CHECK();
