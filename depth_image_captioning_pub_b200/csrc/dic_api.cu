@@ -497,6 +497,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     z.add(gr.fbeta_w, sizeof(float) * (size_t)D * H);
     z.add(gr.enc_att_w, sizeof(float) * (size_t)A * D);
     z.add(gr.embed_w, sizeof(float) * (size_t)V * E);
+    z.add(dzg, sizeof(float) * (size_t)B * D);         // red.add target of the per-step dzg GEMM halves (re-zeroed by its reader)
     DIC_TRY(launch_zero_many(z, st));
   }
 
@@ -536,7 +537,6 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   if (dh_splits < 1) dh_splits = 1;
   const bool dzg_split_ok = is_bf16 && tc_enabled() && cdiv(4 * H, kTcBK) >= 2 * kDzgSplits && D % 8 == 0 &&
                             (long long)B * D >= 128LL * 128LL;
-  if (dzg_split_ok) DIC_CUDA(cudaMemsetAsync(dzg, 0, sizeof(float) * (size_t)B * D, st));
   int offs[DIC_MAX_STEPS + 1];
   offs[0] = 0;
   for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + sizes.n[t];
