@@ -856,6 +856,8 @@ struct Datt1Args {
 constexpr int kDatt1TT = 32;
 template <typename ST>
 __global__ void __launch_bounds__(128) datt1_kernel(const Datt1Args p) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ __align__(16) float a2_s[kDatt1TT][128];
   __shared__ __align__(16) float de_s[kDatt1TT][32];
   const int b = blockIdx.y;
@@ -923,7 +925,7 @@ template <typename ST>
 inline int launch_datt1(const Datt1Args& p, cudaStream_t st) {
   dim3 grid(cdiv(p.L, 32), p.B);
   ProfScope prof(P_DATT1, st, (double)p.B * p.L * p.A * sizeof(ST) * 2);
-  datt1_kernel<ST><<<grid, 128, 0, st>>>(p);
+  DIC_CUDA(launch_pdl(datt1_kernel<ST>, grid, dim3(128), 0, st, p));
   DIC_LAUNCH_CHECK();
   return 0;
 }

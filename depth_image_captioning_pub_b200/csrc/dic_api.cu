@@ -79,6 +79,8 @@ struct ZeroJobs {
   }
 };
 __global__ void __launch_bounds__(256) zero_many_kernel(const ZeroJobs j) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   const int job = blockIdx.y;
   char* base = reinterpret_cast<char*>(j.p[job]);
   const unsigned long long nb = j.bytes[job];
@@ -93,13 +95,15 @@ __global__ void __launch_bounds__(256) zero_many_kernel(const ZeroJobs j) {
 }
 static int launch_zero_many(const ZeroJobs& j, cudaStream_t st) {
   if (j.n == 0) return 0;
-  zero_many_kernel<<<dim3(64, j.n), 256, 0, st>>>(j);
+  DIC_CUDA(launch_pdl(zero_many_kernel, dim3(64, j.n), dim3(256), 0, st, j));
   DIC_LAUNCH_CHECK();
   return 0;
 }
 // column sums of G -> the four bias gradients they belong to (b_ih and b_hh share the gate slice)
 __global__ void __launch_bounds__(256) bias_scatter_kernel(const float* __restrict__ gsum, float* b_ih, float* b_hh, float* dec_att_b,
                                                            float* fbeta_b, int H4, int A, int D) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < H4) { const float v = gsum[i]; b_ih[i] = v; b_hh[i] = v; }
   else if (i < H4 + A) dec_att_b[i - H4] = gsum[i];
@@ -346,9 +350,8 @@ static int decoder_forward_impl(const dic_dims& d, int attn_mode, const void* pa
   // all-step embedding gather (depth_models.py:160)
   {
     dim3 grid(cdiv(B * d.E, 256), T);
-    embed_gather_tf_kernel<ST><<<grid, 256, 0, st>>>(reinterpret_cast<const ST*>(pk.Emb()), captions,
-                                                     cap_stride, XH, (long long)XW, (long long)B * XW, B,
-                                                     d.E, d.V, sizes, T);
+    DIC_CUDA(launch_pdl(embed_gather_tf_kernel<ST>, grid, dim3(256), 0, st, reinterpret_cast<const ST*>(pk.Emb()), captions,
+                        cap_stride, XH, (long long)XW, (long long)B * XW, B, d.E, d.V, sizes, T));
     DIC_LAUNCH_CHECK();
   }
 
@@ -632,7 +635,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     // bf16 operands [dh0|dc0] and mean_l F -> two tensor-core GEMMs; the bias gradient rides on the cast
     bf16* dhc16 = reinterpret_cast<bf16*>(ws + lay.dhc16);
     const bf16* mean16 = reinterpret_cast<const bf16*>(ws + lay.meanF16);
-    dhc_prep_kernel<<<cdiv(2 * H, 32), 256, 0, st>>>(dh, dc, dhc16, gr.init_b, B, H);
+    DIC_CUDA(launch_pdl(dhc_prep_kernel, dim3(cdiv(2 * H, 32)), dim3(256), 0, st, dh, dc, dhc16, gr.init_b, B, H));
     DIC_LAUNCH_CHECK();
     {
       GemmArgs g = gemm_args_nt(dhc16, 1, 0, mean16, 1, 0, gr.init_w, 0, D, 2 * H, D, B, nullptr);
@@ -665,7 +668,8 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   {
     float* gsum = reinterpret_cast<float*>(ws + lay.tmpvec);
     DIC_TRY(launch_colsum(G, is_bf16, (int)TB, (int)GW, GW, gsum, st));
-    bias_scatter_kernel<<<cdiv(4 * H + A + D, 256), 256, 0, st>>>(gsum, gr.b_ih, gr.b_hh, gr.dec_att_b, gr.fbeta_b, 4 * H, A, D);
+    DIC_CUDA(launch_pdl(bias_scatter_kernel, dim3(cdiv(4 * H + A + D, 256)), dim3(256), 0, st, (const float*)gsum, gr.b_ih, gr.b_hh,
+                        gr.dec_att_b, gr.fbeta_b, 4 * H, A, D));
     DIC_LAUNCH_CHECK();
   }
 
@@ -689,7 +693,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     DIC_TRY(gemm(g, st));
     // (gr.embed_w was cleared with the other accumulation targets at the top)
     dim3 grid(cdiv(B * E, 256), T);
-    embed_scatter_add_kernel<<<grid, 256, 0, st>>>(dXemb, captions, cap_stride, gr.embed_w, B, E, V, sizes, T);
+    DIC_CUDA(launch_pdl(embed_scatter_add_kernel, grid, dim3(256), 0, st, dXemb, captions, cap_stride, gr.embed_w, B, E, V, sizes, T));
     DIC_LAUNCH_CHECK();
   }
 
@@ -1336,7 +1340,7 @@ int dic_pack_weights(const dic_dims* dims, int dtype, const dic_params* p, void*
   add(p->lin_b, d.V, base + lay.b_out, d.V, 0, 1, d.V);
   add(p->full_att_w, d.A, base + lay.w_full, d.A, 0, 1, d.A);
   add(p->full_att_b, 1, base + lay.b_full, 1, 0, 1, 1);
-  pack_jobs_kernel<<<dim3(296, jobs.n), 256, 0, st>>>(jobs);
+  DIC_CUDA(launch_pdl(pack_jobs_kernel, dim3(296, jobs.n), dim3(256), 0, st, jobs));
   DIC_LAUNCH_CHECK();
   return 0;
 }
@@ -1367,7 +1371,7 @@ int dic_adamw_step(int n, float* const* params, const float* const* grads, float
     long long bx = (biggest / 4 + 255) / 256;
     if (bx > 148) bx = 148;
     if (bx < 1) bx = 1;
-    adamw_kernel<<<dim3((unsigned)bx, a.count), 256, 0, st>>>(a);
+    DIC_CUDA(launch_pdl(adamw_kernel, dim3((unsigned)bx, a.count), dim3(256), 0, st, a));
     DIC_LAUNCH_CHECK();
   }
   return 0;

@@ -37,6 +37,8 @@ __device__ __forceinline__ int loss_target(const LossArgs& p, int r) {
 
 // number of non-ignored targets (the mean's denominator), one CTA
 __global__ void __launch_bounds__(1024) loss_count_kernel(const LossArgs p) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ float scratch[64];
   float c = 0.f;
   for (int r = threadIdx.x; r < p.N; r += 1024) c += (loss_target(p, r) != p.ignore_index) ? 1.f : 0.f;
@@ -49,6 +51,8 @@ __global__ void __launch_bounds__(1024) loss_count_kernel(const LossArgs p) {
 constexpr int kCeThreads = 256;     // threads per logits row (512 measured 7% slower)
 template <typename ST>
 __global__ void __launch_bounds__(kCeThreads) loss_ce_row_kernel(const LossArgs p, int staged) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   extern __shared__ __align__(16) float row_s[];
   __shared__ float scratch[64];
   const int r = blockIdx.x, tid = threadIdx.x, V = p.V;
@@ -172,6 +176,8 @@ __global__ void __launch_bounds__(kCeThreads) loss_ce_row_kernel(const LossArgs 
 // passes with 5 resident per SM).
 constexpr int kCeRegChunks = 5;     // 16-byte chunks per thread: 256 threads x 5 x 8 = 10240 columns
 __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ float scratch[64];
   const int r = blockIdx.x, tid = threadIdx.x, V = p.V;
   const bf16* lb = reinterpret_cast<const bf16*>(p.logits) + (size_t)r * V;
@@ -248,6 +254,8 @@ __global__ void __launch_bounds__(256) loss_ce_row_reg_kernel(const LossArgs p) 
 // doubly-stochastic regulariser, one CTA per image: S[l] = sum_t alpha[b,t,l];
 // regsq[b] = sum_l (1-S)^2 ; d_alpha[b,t,l] = -2 lam (1-S[l]) / (B L) for every t
 __global__ void __launch_bounds__(256) loss_reg_kernel(const LossArgs p) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ float scratch[64];
   const int b = blockIdx.x;
   const float* al = p.alphas + (size_t)b * p.T * p.L;
@@ -269,6 +277,8 @@ __global__ void __launch_bounds__(256) loss_reg_kernel(const LossArgs p) {
 
 // loss = sum(nll)/count + lam * sum(regsq)/(B L); one CTA, fixed reduction order
 __global__ void __launch_bounds__(1024) loss_final_kernel(const LossArgs p) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ float scratch[64];
   float a = 0.f;
   for (int r = threadIdx.x; r < p.N; r += 1024) a += p.nll[r];
@@ -314,7 +324,7 @@ inline int launch_caption_loss(LossArgs p, void* workspace, cudaStream_t st) {
   p.nll = reinterpret_cast<float*>(ws);
   p.count = reinterpret_cast<float*>(ws + align_up(sizeof(float) * (size_t)p.N, 256));
   p.regsq = reinterpret_cast<float*>(ws + align_up(sizeof(float) * (size_t)p.N, 256) + 256);
-  loss_count_kernel<<<1, 1024, 0, st>>>(p);
+  DIC_CUDA(launch_pdl(loss_count_kernel, dim3(1), dim3(1024), 0, st, p));
   DIC_LAUNCH_CHECK();
   const size_t row_bytes = sizeof(float) * (size_t)p.V;
   const int staged = row_bytes <= 200 * 1024 ? 1 : 0;
@@ -328,16 +338,16 @@ inline int launch_caption_loss(LossArgs p, void* workspace, cudaStream_t st) {
   {
     ProfScope prof(P_LOSS, st, (double)p.N * p.V * ((p.logits_bf16 ? 2 : 4) + sizeof(ST)));
     if (sizeof(ST) == 2 && p.logits_bf16 && p.V % 8 == 0 && p.V <= 256 * 8 * kCeRegChunks && ce_reg_enabled())
-      loss_ce_row_reg_kernel<<<p.N, 256, 0, st>>>(p);
+      DIC_CUDA(launch_pdl(loss_ce_row_reg_kernel, dim3(p.N), dim3(256), 0, st, p));
     else
-      loss_ce_row_kernel<ST><<<p.N, kCeThreads, staged ? row_bytes : 0, st>>>(p, staged);
+      DIC_CUDA(launch_pdl(loss_ce_row_kernel<ST>, dim3(p.N), dim3(kCeThreads), staged ? row_bytes : 0, st, p, staged));
     DIC_LAUNCH_CHECK();
   }
   if (p.alphas && p.lam != 0.f) {
-    loss_reg_kernel<<<p.B, 256, 0, st>>>(p);
+    DIC_CUDA(launch_pdl(loss_reg_kernel, dim3(p.B), dim3(256), 0, st, p));
     DIC_LAUNCH_CHECK();
   }
-  loss_final_kernel<<<1, 1024, 0, st>>>(p);
+  DIC_CUDA(launch_pdl(loss_final_kernel, dim3(1), dim3(1024), 0, st, p));
   DIC_LAUNCH_CHECK();
   return 0;
 }

@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256) fuse_feats_kernel(const TIN* __restrict__
                                                          const TIN* __restrict__ dep, ST* __restrict__ fsum,
                                                          float* __restrict__ meanF, bf16* __restrict__ mean16,
                                                          int L, int D) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   const int b = blockIdx.y;
   const int d = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (d >= D) return;
@@ -73,11 +75,11 @@ inline int launch_fuse_feats(const void* rgb, const void* dep, int feat_bf16, ST
   dim3 grid(cdiv(D, 1024), B);
   ProfScope prof(P_FUSE, st);
   if (feat_bf16)
-    fuse_feats_kernel<bf16, ST><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(rgb),
-                                                     reinterpret_cast<const bf16*>(dep), fsum, meanF, mean16, L, D);
+    DIC_CUDA(launch_pdl(fuse_feats_kernel<bf16, ST>, grid, dim3(256), 0, st, reinterpret_cast<const bf16*>(rgb),
+                        reinterpret_cast<const bf16*>(dep), fsum, meanF, mean16, L, D));
   else
-    fuse_feats_kernel<float, ST><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(rgb),
-                                                      reinterpret_cast<const float*>(dep), fsum, meanF, mean16, L, D);
+    DIC_CUDA(launch_pdl(fuse_feats_kernel<float, ST>, grid, dim3(256), 0, st, reinterpret_cast<const float*>(rgb),
+                        reinterpret_cast<const float*>(dep), fsum, meanF, mean16, L, D));
   DIC_LAUNCH_CHECK();
   return 0;
 }
@@ -88,6 +90,8 @@ inline int launch_fuse_feats(const void* rgb, const void* dep, int feat_bf16, ST
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ src, int src_bf16, int R,
                                                      int C, long long ld, int rows_per_block,
                                                      float* __restrict__ dst) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -118,6 +122,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ sr
 // loads, a warp covers 512 contiguous bytes of a row), 8 row groups per CTA, 4 rows in flight per thread
 __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restrict__ src, int R, int C, long long ld,
                                                             int rows_per_block, float* __restrict__ dst) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ float red[8][32][9];
   const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + lane * 8;
@@ -172,7 +178,7 @@ inline int launch_colsum(const void* src, int src_bf16, int R, int C, long long 
     if (chunks < 1) chunks = 1;
     const int rpb = cdiv(cdiv(R, chunks), 8) * 8;
     dim3 grid(ctiles, cdiv(R, rpb));
-    colsum_bf16x8_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(src), R, C, ld, rpb, dst);
+    DIC_CUDA(launch_pdl(colsum_bf16x8_kernel, grid, dim3(256), 0, st, reinterpret_cast<const bf16*>(src), R, C, ld, rpb, dst));
     DIC_LAUNCH_CHECK();
     return 0;
   }
@@ -180,7 +186,7 @@ inline int launch_colsum(const void* src, int src_bf16, int R, int C, long long 
   if (chunks > 1024) chunks = 1024;
   const int rpb = cdiv(R, chunks);
   dim3 grid(cdiv(C, 32), cdiv(R, rpb));
-  colsum_kernel<<<grid, 256, 0, st>>>(src, src_bf16, R, C, ld, rpb, dst);
+  DIC_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, st, src, src_bf16, R, C, ld, rpb, dst));
   DIC_LAUNCH_CHECK();
   return 0;
 }
@@ -192,6 +198,8 @@ __global__ void __launch_bounds__(256) embed_gather_tf_kernel(const ST* __restri
                                                               int cap_stride, ST* __restrict__ X,
                                                               long long x_row, long long x_step, int B,
                                                               int E, int V, StepSizes sizes, int T) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   const int t = blockIdx.y;
   const int n = sizes.n[t];
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n * E; i += gridDim.x * 256) {
@@ -208,6 +216,8 @@ __global__ void __launch_bounds__(256) embed_scatter_add_kernel(const float* __r
                                                                 int cap_stride, float* __restrict__ dEmb,
                                                                 int B, int E, int V, StepSizes sizes,
                                                                 int T) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   const int t = blockIdx.y;
   const int n = sizes.n[t];
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n * E; i += gridDim.x * 256) {
@@ -276,6 +286,8 @@ struct PackJobs {
   int n;
 };
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJobs jobs) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   const PackJob& jb = jobs.j[blockIdx.y];
   const size_t n = (size_t)jb.R * jb.C;
   const bool dense = jb.src_ld == jb.C && jb.dst_ld == jb.C;
@@ -322,6 +334,8 @@ struct AdamWJobs {
   float eps;
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamWJobs a) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   const int j = blockIdx.y;
   float* __restrict__ p = a.p[j];
   const float* __restrict__ g = a.g[j];
@@ -366,6 +380,8 @@ __global__ void __launch_bounds__(256) add_vec_kernel(const float* a, const floa
 // row groups).
 __global__ void __launch_bounds__(256) dhc_prep_kernel(const float* __restrict__ dh, const float* __restrict__ dc,
                                                        bf16* __restrict__ dhc16, float* __restrict__ db, int B, int H) {
+  pdl_wait();          // launched programmatically (launch_pdl): nothing of a predecessor is touched before this
+  pdl_trigger();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;          // column in [0, 2H)
