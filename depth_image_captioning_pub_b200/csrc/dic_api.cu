@@ -69,7 +69,7 @@ static int gemm(const GemmArgs& g, cudaStream_t st) {
 // Several buffers cleared by ONE launch.  The backward used to enqueue a cudaMemsetAsync in front of each of its
 // twelve split-K / accumulation targets and four device-to-device copies for the bias slices: every such node is
 // its own small grid with a full (non-programmatic) dependency on both sides, ~3 us of stream time each.
-constexpr int kZeroJobsMax = 12;
+constexpr int kZeroJobsMax = 20;
 struct ZeroJobs {
   void* p[kZeroJobsMax];
   unsigned long long bytes[kZeroJobsMax];
@@ -501,6 +501,12 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     z.add(gr.enc_att_w, sizeof(float) * (size_t)A * D);
     z.add(gr.embed_w, sizeof(float) * (size_t)V * E);
     z.add(dzg, sizeof(float) * (size_t)B * D);         // red.add target of the per-step dzg GEMM halves (re-zeroed by its reader)
+    // destinations of the column-sum kernels (atomic partial sums)
+    z.add(gr.lin_b, sizeof(float) * V);
+    z.add(ws + lay.tmpvec, sizeof(float) * GW);
+    z.add(gr.full_att_w, sizeof(float) * A);
+    z.add(gr.full_att_b, sizeof(float) * 1);
+    z.add(gr.enc_att_b, sizeof(float) * A);
     DIC_TRY(launch_zero_many(z, st));
   }
 
@@ -529,7 +535,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     GemmArgs g = gemm_args_nt(dl, dl_bf16, 0, Hdrop, is_bf16, 0, gr.lin_w, 0, H, V, H, total, nullptr);
     g.a_m = 1; g.a_k = V; g.b_n = 1; g.b_k = H;
     DIC_TRY(gemm_splitk(g, st, true));
-    DIC_TRY(launch_colsum(dl, dl_bf16, total, V, V, gr.lin_b, st));   // bf16 mode: half the bytes
+    DIC_TRY(launch_colsum(dl, dl_bf16, total, V, V, gr.lin_b, st, true));   // bf16 mode: half the bytes
     if (cudaEvent_t ev = g_grads_lin_event.exchange(nullptr)) DIC_CUDA(cudaEventRecord(ev, st));
   }
 
@@ -667,7 +673,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   // (one pass over G, then the four slices are copied out)
   {
     float* gsum = reinterpret_cast<float*>(ws + lay.tmpvec);
-    DIC_TRY(launch_colsum(G, is_bf16, (int)TB, (int)GW, GW, gsum, st));
+    DIC_TRY(launch_colsum(G, is_bf16, (int)TB, (int)GW, GW, gsum, st, true));
     DIC_CUDA(launch_pdl(bias_scatter_kernel, dim3(cdiv(4 * H + A + D, 256)), dim3(256), 0, st, (const float*)gsum, gr.b_ih, gr.b_hh,
                         gr.dec_att_b, gr.fbeta_b, 4 * H, A, D));
     DIC_LAUNCH_CHECK();
@@ -698,8 +704,8 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
   }
 
   // full_att
-  DIC_TRY(launch_colsum(dwfull_part, 0, (int)TB, A, A, gr.full_att_w, st));
-  DIC_TRY(launch_colsum(dbfull_part, 0, (int)TB, 1, 1, gr.full_att_b, st));
+  DIC_TRY(launch_colsum(dwfull_part, 0, (int)TB, A, A, gr.full_att_w, st, true));
+  DIC_TRY(launch_colsum(dbfull_part, 0, (int)TB, 1, 1, gr.full_att_b, st, true));
 
   if (cudaEvent_t ev = g_grads_mid_event.exchange(nullptr)) DIC_CUDA(cudaEventRecord(ev, st));
 
@@ -709,7 +715,7 @@ static int decoder_backward_impl(const dic_dims& d, int attn_mode, const void* p
     da.att1 = att1; da.hp_all = HP; da.de_all = de; da.w_full = pk.w_full(); da.datt1 = datt1;
     da.B = B; da.L = L; da.D = D; da.A = A; da.T = T; da.sizes = sizes;
     DIC_TRY(launch_datt1<ST>(da, st));
-    DIC_TRY(launch_colsum(datt1, is_bf16, B * L, A, A, gr.enc_att_b, st));
+    DIC_TRY(launch_colsum(datt1, is_bf16, B * L, A, A, gr.enc_att_b, st, true));
     DIC_TRY(wgrad(datt1, A, A, F, D, D, B * L, gr.enc_att_w, D));
   }
 

@@ -166,10 +166,11 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16* __restri
   }
 }
 
+// zeroed: the caller has cleared dst already (the backward clears all its accumulation targets in one launch)
 inline int launch_colsum(const void* src, int src_bf16, int R, int C, long long ld, float* dst,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool zeroed = false) {
   ProfScope prof(P_COLSUM, st);
-  DIC_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * C, st));
+  if (!zeroed) DIC_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * C, st));
   if (R <= 0 || C <= 0) return 0;
   if (src_bf16 && C >= 256 && C % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const int ctiles = cdiv(C, 256);
